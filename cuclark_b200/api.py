@@ -1,0 +1,264 @@
+"""Host-side mirror of the reference's GPU driver class over the C ABI.
+
+``CuClarkDB`` follows ``CuClarkDB<HKMERr>`` of the reference
+(src/CuClarkDB.cuh:98-150): same method names, argument meaning and error
+behaviour (``read`` returns False when a database file is missing; CUDA
+failures raise), so the parity tests read like a test of the reference class.
+Everything goes through ``libcuclark_b200.so`` (include/cuclark_b200.h) with
+ctypes; there is no Python or CPU implementation behind it — if the library
+is missing or there is no GPU the calls fail loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libcuclark_b200.so")
+
+HTSIZE_FULL = 1610612741     # src/parameters.hh:39
+HTSIZE_LIGHT = 57777779      # src/parameters_light_hh:40
+MAXHITS_FULL = 15            # src/parameters.hh:44
+MAXHITS_LIGHT = 23           # src/parameters_light_hh:45
+FINAL_ROW = 5                # m_finalResultsRowSize, src/CuCLARK_hh.hh:1593
+
+# every symbol include/cuclark_b200.h declares
+ABI_SYMBOLS = [
+    "cuclark_last_error", "cuclark_version", "cuclark_create", "cuclark_destroy",
+    "cuclark_load_db_files", "cuclark_load_db_arrays", "cuclark_build_db_synthetic",
+    "cuclark_get_stats", "cuclark_sync_stats",
+    "cuclark_batches_alloc", "cuclark_batch_buffers", "cuclark_batch_ready", "cuclark_batch_query",
+    "cuclark_batch_wait", "cuclark_batches_free",
+    "cuclark_classify_host", "cuclark_classify_device", "cuclark_merge_rows_device",
+    "cuclark_synth_reads_device", "cuclark_gather_bench",
+]
+
+
+class CuclarkError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"cuclark_b200 error {code}: {msg}")
+        self.code = code
+
+
+class Config(C.Structure):
+    _fields_ = [("k", C.c_int), ("htsize", C.c_uint64), ("key_bytes", C.c_int), ("n_targets", C.c_int),
+                ("row_pairs", C.c_int), ("device", C.c_int), ("shard_index", C.c_int), ("shard_count", C.c_int),
+                ("bucket_load", C.c_double), ("layout", C.c_int)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("n_entries", C.c_uint64), ("n_buckets", C.c_uint64), ("n_local_buckets", C.c_uint64),
+                ("table_bytes", C.c_uint64), ("n_spilled", C.c_uint64), ("n_spill_buckets", C.c_uint64),
+                ("layout", C.c_int), ("k", C.c_int), ("lookups", C.c_uint64), ("dense_reads", C.c_uint64),
+                ("truncated_rows", C.c_uint64), ("last_kernel_ms", C.c_double)]
+
+    def as_dict(self):
+        return {f: getattr(self, f) for f, _ in self._fields_}
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen libcuclark_b200.so and declare the prototypes. Raises if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FileNotFoundError(
+            f"{LIB_PATH} is missing: build it with `python -m cuclark_b200.build` "
+            "(there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    u64, u32, u16, u8, sz, vp, ci = C.c_uint64, C.c_uint32, C.c_uint16, C.c_uint8, C.c_size_t, C.c_void_p, C.c_int
+    P = C.POINTER
+    lib.cuclark_last_error.restype = C.c_char_p
+    lib.cuclark_version.restype = ci
+    lib.cuclark_create.argtypes = [P(Config), P(vp)]
+    lib.cuclark_destroy.argtypes = [vp]
+    lib.cuclark_load_db_files.argtypes = [vp, C.c_char_p, ci]
+    lib.cuclark_load_db_arrays.argtypes = [vp, vp, vp, vp, u64, ci]
+    lib.cuclark_build_db_synthetic.argtypes = [vp, u32, u32, u64, ci]
+    lib.cuclark_get_stats.argtypes = [vp, P(Stats)]
+    lib.cuclark_sync_stats.argtypes = [vp, vp]
+    lib.cuclark_batches_alloc.argtypes = [vp, ci, sz, sz, ci]
+    lib.cuclark_batch_buffers.argtypes = [vp, ci, P(vp), P(vp), P(vp), P(vp)]
+    lib.cuclark_batch_ready.argtypes = [vp, ci, sz, sz]
+    lib.cuclark_batch_query.argtypes = [vp, ci]
+    lib.cuclark_batch_wait.argtypes = [vp, ci]
+    lib.cuclark_batches_free.argtypes = [vp]
+    lib.cuclark_classify_host.argtypes = [vp, vp, vp, sz, vp, vp]
+    lib.cuclark_classify_device.argtypes = [vp, vp, vp, sz, vp, vp, vp]
+    lib.cuclark_merge_rows_device.argtypes = [vp, vp, ci, sz, vp, vp, vp]
+    lib.cuclark_synth_reads_device.argtypes = [vp, u32, u32, u32, u64, u64, sz, ci, ci, ci, vp, vp, vp]
+    lib.cuclark_gather_bench.argtypes = [vp, u64, ci, ci, ci, P(C.c_double)]
+    for name in ABI_SYMBOLS:
+        fn = getattr(lib, name)
+        if name != "cuclark_last_error":
+            fn.restype = ci
+    _lib = lib
+    return lib
+
+
+def key_bytes_for(k: int, htsize: int) -> int:
+    """Width of a .ky element as the reference CLI picks it (src/main.cc:278-316)."""
+    import math
+    t_b = int(math.log(htsize) / math.log(4.0))
+    return 2 if k <= t_b + 8 else 4 if k <= t_b + 16 else 8
+
+
+def _np_from(ptr, n, dtype):
+    if not ptr or n == 0:
+        return np.zeros(0, dtype)
+    ct = {np.uint32: C.c_uint32, np.uint16: C.c_uint16}[dtype]
+    return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ct)), shape=(n,))
+
+
+class CuClarkDB:
+    """Mirror of ``CuClarkDB<HKMERr>`` (src/CuClarkDB.cuh:98-150) for ONE device.
+
+    ctor(numDevices, k, numBatches, numTargets) becomes
+    ``CuClarkDB(k, n_targets, light=..., device=..., shard=(i, n))``: the
+    variant is a run-time choice and multi-GPU is one process per GPU.
+    """
+
+    def __init__(self, k: int, n_targets: int, light: bool = False, device: int = 0, shard=(0, 1),
+                 row_pairs: int = 0, bucket_load: float = 0.0, layout: int = 0, htsize: int | None = None):
+        self._lib = load_library()
+        self.htsize = htsize if htsize is not None else (HTSIZE_LIGHT if light else HTSIZE_FULL)
+        self.k = k
+        self.n_targets = n_targets
+        self.row_pairs = row_pairs or (MAXHITS_LIGHT if self.htsize == HTSIZE_LIGHT else MAXHITS_FULL)
+        self.row_size = 2 * self.row_pairs + 2          # m_resultRowSize, src/CuCLARK_hh.hh:1586-1590
+        self.key_bytes = key_bytes_for(k, self.htsize)
+        cfg = Config(k, self.htsize, self.key_bytes, n_targets, self.row_pairs, device, shard[0], shard[1],
+                     bucket_load, layout)
+        h = C.c_void_p()
+        self._h = None
+        self._check(self._lib.cuclark_create(C.byref(cfg), C.byref(h)))
+        self._h = h
+        self._batches = 0
+        self._want_rows = False
+
+    # -- plumbing -------------------------------------------------------------
+    def _check(self, rc: int):
+        if rc != 0:
+            raise CuclarkError(rc, self._lib.cuclark_last_error().decode())
+
+    def close(self):
+        if self._h:
+            self._lib.cuclark_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- database (CuClarkDB::read, src/CuClarkDB.cu:462) ------------------------
+    def read(self, filename: str, mod_collision: int = 1) -> bool:
+        """Load ``<filename>.sz/.ky/.lb``; False if a file is missing (the
+        reference's contract, the caller then rebuilds or exits)."""
+        rc = self._lib.cuclark_load_db_files(self._h, filename.encode(), mod_collision)
+        if rc == -4:      # CUCLARK_ERR_IO
+            return False
+        self._check(rc)
+        return True
+
+    def load_arrays(self, sz, ky, lb, mod_collision: int = 1):
+        sz = np.ascontiguousarray(sz, np.uint8)
+        lb = np.ascontiguousarray(lb, np.uint16)
+        ky = np.ascontiguousarray(ky)
+        assert ky.dtype.itemsize == self.key_bytes, "key dtype must match the reference's key width for this k"
+        assert sz.size == self.htsize
+        self._check(self._lib.cuclark_load_db_arrays(self._h, sz.ctypes.data, ky.ctypes.data, lb.ctypes.data,
+                                                      ky.size, mod_collision))
+
+    def build_synthetic(self, seed: int, n_targets: int, genome_len: int, light_gap: int = 0):
+        self._check(self._lib.cuclark_build_db_synthetic(self._h, seed, n_targets, genome_len, light_gap))
+
+    def swapDbParts(self) -> bool:
+        """The table is fully resident: there is never another part (src/CuClarkDB.cu:814-858)."""
+        return False
+
+    def sync(self) -> bool:
+        return True
+
+    def stats(self, sync_stream=None, sync: bool = False) -> dict:
+        if sync:
+            self._check(self._lib.cuclark_sync_stats(self._h, sync_stream))
+        s = Stats()
+        self._check(self._lib.cuclark_get_stats(self._h, C.byref(s)))
+        return s.as_dict()
+
+    # -- batches (malloc/readyBatch/queryBatch/waitForBatch/freeBatchMemory) ------
+    def malloc(self, n_batches: int, max_reads: int, max_containers: int, is_extended: bool = False):
+        """Allocate pinned + device buffers; returns per-batch numpy views
+        (reads_ptr, containers, final, rows) over the library's pinned memory."""
+        self._check(self._lib.cuclark_batches_alloc(self._h, n_batches, max_reads, max_containers, int(is_extended)))
+        self._batches, self._want_rows = n_batches, is_extended
+        views = []
+        for b in range(n_batches):
+            p, c, f, r = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+            self._check(self._lib.cuclark_batch_buffers(self._h, b, C.byref(p), C.byref(c), C.byref(f), C.byref(r)))
+            views.append((_np_from(p, max_reads + 1, np.uint32), _np_from(c, max_containers, np.uint16),
+                          _np_from(f, max_reads * FINAL_ROW, np.uint16).reshape(max_reads, FINAL_ROW),
+                          _np_from(r, max_reads * self.row_size, np.uint16).reshape(max_reads, self.row_size)
+                          if is_extended else None))
+        return views
+
+    def readyBatch(self, batch_id: int, n_reads: int, container_count: int) -> bool:
+        self._check(self._lib.cuclark_batch_ready(self._h, batch_id, n_reads, container_count))
+        return True
+
+    def queryBatch(self, batch_id: int, is_extended: bool = False, is_followup: bool = False) -> bool:
+        self._check(self._lib.cuclark_batch_query(self._h, batch_id))
+        return True
+
+    def waitForBatch(self, batch_id: int) -> bool:
+        self._check(self._lib.cuclark_batch_wait(self._h, batch_id))
+        return True
+
+    def freeBatchMemory(self):
+        self._check(self._lib.cuclark_batches_free(self._h))
+        self._batches = 0
+
+    # -- one-shot ------------------------------------------------------------------
+    def classify(self, reads_ptr, containers, want_rows: bool = False):
+        """Host arrays in (reference packed format), host arrays out."""
+        ptr = np.ascontiguousarray(reads_ptr, np.uint32)
+        cont = np.ascontiguousarray(containers, np.uint16)
+        n = ptr.size - 1
+        final = np.zeros((n, FINAL_ROW), np.uint16)
+        rows = np.zeros((n, self.row_size), np.uint16) if want_rows else None
+        self._check(self._lib.cuclark_classify_host(self._h, ptr.ctypes.data, cont.ctypes.data if cont.size else None, n,
+                                                     final.ctypes.data, rows.ctypes.data if want_rows else None))
+        return final, rows
+
+    def classify_device(self, d_ptr: int, d_cont: int, n_reads: int, d_final: int = 0, d_rows: int = 0, stream: int = 0):
+        self._check(self._lib.cuclark_classify_device(self._h, d_ptr, d_cont, n_reads, d_final or None, d_rows or None,
+                                                       stream or None))
+
+    def merge_rows_device(self, d_parts: int, n_parts: int, n_reads: int, d_rows_out: int = 0, d_final: int = 0,
+                          stream: int = 0):
+        self._check(self._lib.cuclark_merge_rows_device(self._h, d_parts, n_parts, n_reads, d_rows_out or None,
+                                                         d_final or None, stream or None))
+
+    def synth_reads_device(self, seed, genome_seed, n_targets, genome_len, first_read, n_reads, read_len,
+                           pct_random, sub_per_10k, d_ptr: int, d_cont: int, stream: int = 0):
+        self._check(self._lib.cuclark_synth_reads_device(self._h, seed, genome_seed, n_targets, genome_len, first_read,
+                                                          n_reads, read_len, pct_random, sub_per_10k, d_ptr, d_cont,
+                                                          stream or None))
+
+    def gather_bench(self, n_probes: int, bytes_per_probe: int = 32, ilp: int = 4, iters: int = 5) -> float:
+        ms = C.c_double()
+        self._check(self._lib.cuclark_gather_bench(self._h, n_probes, bytes_per_probe, ilp, iters, C.byref(ms)))
+        return ms.value

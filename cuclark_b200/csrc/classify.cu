@@ -1,0 +1,521 @@
+// cuclark_b200 — the classification kernels.
+//
+// Replaces queryKernel/queryElement/mergeKernel/resultKernel of the reference
+// (src/CuClarkDB.cu:1045-1471). One WARP per read (the reference: one 64-thread
+// block per read, one thread per k-mer, each re-reading up to 8 containers):
+//   * lane j keeps 32 nucleotides of the current part as one 64-bit word; a
+//     k-mer is a funnel shift of two neighbouring words fetched by shuffle
+//     (no shared-memory staging, no per-thread re-assembly);
+//   * canonical k-mer -> (home bucket, exact quotient) -> ONE 256-bit load of
+//     the 32-byte sector bucket; ILP_ROUNDS independent probes per lane are in
+//     flight before any is consumed;
+//   * per-read target counts live in a 64-slot per-warp hash table in shared
+//     memory (the reference zeroes and scans numTargets counters per read), with
+//     a register fast path while a read has hit a single target;
+//   * top-1/top-2 by one warp max-reduction each over (hits << 16 | ~target):
+//     identical to the reference's ascending scan with strict '>' (lowest
+//     target index wins ties); sparse rows are emitted in
+//     ascending target order only when asked for.
+// Reads that hit more than 64 distinct targets are handed to an exact dense
+// fallback kernel (the reference is undefined beyond MAXHITS).
+#include <algorithm>
+
+#include "internal.h"
+#include "synth.cuh"
+
+namespace cuclark {
+
+namespace {
+
+constexpr int WARPS_PER_BLOCK = 8;
+constexpr int TSLOTS = 64;            // per-warp hash slots
+constexpr int ILP_ROUNDS = 4;         // independent probes per lane
+constexpr int CHUNK_ROUNDS = 31;      // rounds of 32 k-mers served by one set of 32 words
+constexpr int MAX_ROW_PAIRS = 63;
+constexpr uint32_t EMPTY = 0xFFFFFFFFu;
+
+struct ClassifyParams {
+    TableView t;
+    const uint32_t* reads_ptr;
+    const uint16_t* cont;
+    uint32_t n_reads;
+    uint16_t* final5;
+    uint16_t* rows;
+    int row_pairs;
+    uint32_t n_targets;
+    uint32_t* counters;
+    uint32_t* dense_list;
+    uint32_t dense_cap;
+};
+
+__device__ __forceinline__ uint64_t shfl64(uint64_t v, int src) {
+    uint32_t lo = __shfl_sync(0xFFFFFFFFu, (uint32_t)v, src);
+    uint32_t hi = __shfl_sync(0xFFFFFFFFu, (uint32_t)(v >> 32), src);
+    return ((uint64_t)hi << 32) | lo;
+}
+
+// leader-only insert of (label, n) into the warp's table; false if it is full
+__device__ __forceinline__ bool tab_add(uint32_t* tkey, uint32_t* tcnt, uint32_t label, uint32_t n) {
+    uint32_t slot = (label * 0x9E3779B1u) >> 26;          // 6 bits
+#pragma unroll 1
+    for (int i = 0; i < TSLOTS; i++) {
+        const uint32_t old = atomicCAS(&tkey[slot], EMPTY, label);
+        if (old == EMPTY || old == label) { atomicAdd(&tcnt[slot], n); return true; }
+        slot = (slot + 1) & (TSLOTS - 1);
+    }
+    return false;
+}
+
+template <int LAYOUT, bool ROWS>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_classify(const ClassifyParams p) {
+    __shared__ uint32_t s_key[WARPS_PER_BLOCK][TSLOTS];
+    __shared__ uint32_t s_cnt[WARPS_PER_BLOCK][TSLOTS];
+    __shared__ uint16_t s_row[ROWS ? WARPS_PER_BLOCK : 1][ROWS ? 2 * MAX_ROW_PAIRS + 2 : 2];
+
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    uint32_t* tkey = s_key[wib];
+    uint32_t* tcnt = s_cnt[wib];
+    tkey[lane] = EMPTY; tkey[lane + 32] = EMPTY;
+    tcnt[lane] = 0; tcnt[lane + 32] = 0;
+    __syncwarp();
+
+    const TableView& T = p.t;
+    const int k = T.k;
+    const int kshift = 64 - 2 * k;
+    const uint32_t n_warps = gridDim.x * WARPS_PER_BLOCK;
+    const int pitch = 2 * p.row_pairs + 2;
+    unsigned long long my_lookups = 0;
+
+    for (uint32_t read = blockIdx.x * WARPS_PER_BLOCK + wib; read < p.n_reads; read += n_warps) {
+        uint32_t pos = p.reads_ptr[read];
+        const uint32_t end = p.reads_ptr[read + 1];
+        uint32_t first_label = NO_LABEL, first_cnt = 0, total = 0;
+        bool table_mode = false, overflow = false;
+
+        while (pos < end) {
+            const uint32_t L = p.cont[pos];
+            const uint32_t first = pos + 1;
+            pos = first + ((L + 7) >> 3);
+            const int nk = (int)L - k + 1;
+            for (int cb = 0; cb < nk; cb += 32 * CHUNK_ROUNDS) {
+                // lane j: nucleotides [cb + 32j, cb + 32j + 32) of the part, MSB first
+                uint64_t W = 0;
+                {
+                    const uint32_t ci = first + (cb >> 3) + 4 * lane;
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        if (ci + j < pos) W |= (uint64_t)p.cont[ci + j] << (48 - 16 * j);
+                }
+                const int rounds = min(CHUNK_ROUNDS, (nk - cb + 31) >> 5);
+                for (int r0 = 0; r0 < rounds; r0 += ILP_ROUNDS) {
+                    uint64_t q[ILP_ROUNDS], lb[ILP_ROUNDS];
+                    Sector sec[ILP_ROUNDS];
+                    bool live[ILP_ROUNDS];
+#pragma unroll
+                    for (int j = 0; j < ILP_ROUNDS; j++) {
+                        const int i = r0 + j;
+                        const uint64_t hi = shfl64(W, i & 31), lo = shfl64(W, (i + 1) & 31);
+                        uint64_t x = lane ? ((hi << (2 * lane)) | (lo >> (64 - 2 * lane))) : hi;
+                        x >>= kshift;
+                        const bool valid = i < rounds && cb + 32 * i + lane < nk;
+                        uint64_t b;
+                        divmod_M(canonical(x, k), T.M, T.magic, q[j], b);
+                        lb[j] = b - T.lo;
+                        live[j] = valid && lb[j] < T.n_local;
+                        my_lookups += valid;
+                        if (live[j]) sec[j] = load_sector(T.buckets + 2 * lb[j]);
+                    }
+#pragma unroll
+                    for (int j = 0; j < ILP_ROUNDS; j++) {
+                        uint32_t label = NO_LABEL;
+                        if (live[j]) {
+                            label = match_sector<LAYOUT>(sec[j], q[j], 0);
+                            const uint32_t md = sector_maxdisp(sec[j]);
+                            for (uint32_t d = 1; label == NO_LABEL && d <= md; d++) {
+                                uint64_t nb = lb[j] + d;
+                                if (nb >= T.n_local) nb -= T.n_local;
+                                const Sector s2 = load_sector(T.buckets + 2 * nb);
+                                label = match_sector<LAYOUT>(s2, q[j], d);
+                            }
+                            if (label >= p.n_targets) label = NO_LABEL;
+                        }
+                        const uint32_t hitmask = __ballot_sync(0xFFFFFFFFu, label != NO_LABEL);
+                        if (!hitmask) continue;
+                        total += __popc(hitmask);
+                        if (!table_mode) {
+                            if (first_label == NO_LABEL) first_label = __shfl_sync(0xFFFFFFFFu, label, __ffs(hitmask) - 1);
+                            const uint32_t same = __ballot_sync(0xFFFFFFFFu, label == first_label);
+                            if (same == hitmask) { first_cnt += __popc(same); continue; }
+                            table_mode = true;
+                            if (lane == 0 && first_cnt) tab_add(tkey, tcnt, first_label, first_cnt);
+                            __syncwarp();
+                        }
+                        const uint32_t grp = __match_any_sync(0xFFFFFFFFu, label);
+                        bool ok = true;
+                        if (label != NO_LABEL && lane == __ffs(grp) - 1) ok = tab_add(tkey, tcnt, label, __popc(grp));
+                        if (__any_sync(0xFFFFFFFFu, !ok)) overflow = true;
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+
+        // ---- per-read result --------------------------------------------------
+        uint16_t* row = ROWS ? p.rows + (size_t)read * pitch : nullptr;
+        if (overflow) {
+            // exact dense fallback will overwrite; clear the table
+            tkey[lane] = EMPTY; tkey[lane + 32] = EMPTY; tcnt[lane] = 0; tcnt[lane + 32] = 0;
+            __syncwarp();
+            if (lane == 0) {
+                const uint32_t i = atomicAdd(&p.counters[COUNTER_DENSE], 1u);
+                if (i < p.dense_cap) p.dense_list[i] = read;
+            }
+            continue;
+        }
+        uint32_t v_sum, v_i1, v_h1, v_i2, v_h2;
+        if (!table_mode) {
+            const uint32_t h = first_cnt & 0xFFFFu;
+            v_sum = h; v_i1 = h ? first_label + 1 : 0; v_h1 = h; v_i2 = 0; v_h2 = 0;
+            if (ROWS) {
+                for (int i = lane; i < pitch; i += 32) {
+                    uint16_t v = 0;
+                    if (h) v = i == 0 ? 1 : i == 1 ? (uint16_t)first_label : i == 2 ? (uint16_t)h : 0;
+                    row[i] = v;
+                }
+            }
+        } else {
+            // each lane owns slots lane and lane+32
+            const uint32_t l0 = tkey[lane], l1 = tkey[lane + 32];
+            const uint32_t h0 = l0 == EMPTY ? 0 : (tcnt[lane] & 0xFFFFu);
+            const uint32_t h1 = l1 == EMPTY ? 0 : (tcnt[lane + 32] & 0xFFFFu);
+            const uint32_t k0 = h0 ? (h0 << 16) | (0xFFFFu - l0) : 0;
+            const uint32_t k1 = h1 ? (h1 << 16) | (0xFFFFu - l1) : 0;
+            const uint32_t best = __reduce_max_sync(0xFFFFFFFFu, max(k0, k1));
+            const uint32_t e0 = k0 == best ? 0 : k0, e1 = k1 == best ? 0 : k1;
+            const uint32_t second = __reduce_max_sync(0xFFFFFFFFu, max(e0, e1));
+            v_sum = total & 0xFFFFu;
+            v_h1 = best >> 16; v_i1 = best ? (0xFFFFu - (best & 0xFFFFu)) + 1 : 0;
+            v_h2 = second >> 16; v_i2 = second ? (0xFFFFu - (second & 0xFFFFu)) + 1 : 0;
+            if (ROWS) {
+                uint16_t* srow = s_row[wib];
+                for (int i = lane; i < pitch; i += 32) srow[i] = 0;
+                __syncwarp();
+                // rank of each occupied slot = number of occupied slots with a smaller target
+                uint32_t r0 = 0, r1 = 0;
+                for (int s = 0; s < TSLOTS; s++) {
+                    const uint32_t ls = tkey[s];
+                    const bool occ = ls != EMPTY && (tcnt[s] & 0xFFFFu);
+                    r0 += occ && ls < l0;
+                    r1 += occ && ls < l1;
+                }
+                if (h0 && r0 < (uint32_t)p.row_pairs) { srow[1 + 2 * r0] = (uint16_t)l0; srow[2 + 2 * r0] = (uint16_t)h0; }
+                if (h1 && r1 < (uint32_t)p.row_pairs) { srow[1 + 2 * r1] = (uint16_t)l1; srow[2 + 2 * r1] = (uint16_t)h1; }
+                const uint32_t n = __popc(__ballot_sync(0xFFFFFFFFu, h0 != 0)) + __popc(__ballot_sync(0xFFFFFFFFu, h1 != 0));
+                if (lane == 0) {
+                    srow[0] = (uint16_t)n;
+                    if (n > (uint32_t)p.row_pairs) atomicAdd(&p.counters[COUNTER_TRUNC], 1u);
+                }
+                __syncwarp();
+                for (int i = lane; i < pitch; i += 32) row[i] = srow[i];
+            }
+            tkey[lane] = EMPTY; tkey[lane + 32] = EMPTY; tcnt[lane] = 0; tcnt[lane + 32] = 0;
+            __syncwarp();
+        }
+        if (p.final5 && lane < 5) {
+            const uint32_t v = lane == 0 ? v_sum : lane == 1 ? v_i1 : lane == 2 ? v_h1 : lane == 3 ? v_i2 : v_h2;
+            p.final5[(size_t)read * 5 + lane] = (uint16_t)v;
+        }
+    }
+    // one atomic per warp
+    for (int o = 16; o; o >>= 1) my_lookups += __shfl_xor_sync(0xFFFFFFFFu, my_lookups, o);
+    if (lane == 0 && my_lookups)
+        atomicAdd(reinterpret_cast<unsigned long long*>(p.counters + COUNTER_LOOKUPS), my_lookups);
+}
+
+// Exact fallback for reads that hit more than TSLOTS distinct targets: one block
+// per read, dense per-target counters in global scratch (the reference's own
+// scheme, src/CuClarkDB.cu:1064-1074, 1156-1243), ascending scan by thread 0.
+template <int LAYOUT>
+__global__ void __launch_bounds__(256) k_classify_dense(const ClassifyParams p, uint32_t* hist_all) {
+    uint32_t* hist = hist_all + (size_t)blockIdx.x * p.n_targets;
+    const uint32_t n_list = min(p.counters[COUNTER_DENSE], p.dense_cap);
+    const int k = p.t.k;
+    const int pitch = 2 * p.row_pairs + 2;
+    for (uint32_t li = blockIdx.x; li < n_list; li += gridDim.x) {
+        const uint32_t read = p.dense_list[li];
+        uint32_t pos = p.reads_ptr[read];
+        const uint32_t end = p.reads_ptr[read + 1];
+        while (pos < end) {
+            const uint32_t L = p.cont[pos];
+            const uint16_t* c = p.cont + pos + 1;
+            pos += 1 + ((L + 7) >> 3);
+            const int nk = (int)L - k + 1;
+            for (int w = threadIdx.x; w < nk; w += blockDim.x) {
+                uint64_t x = 0;
+                for (int j = 0; j < k; j++) {
+                    const int qn = w + j;
+                    x = (x << 2) | ((c[qn >> 3] >> (2 * (7 - (qn & 7)))) & 3u);
+                }
+                const uint32_t label = table_lookup<LAYOUT>(p.t, canonical(x, k));
+                if (label < p.n_targets) atomicAdd(&hist[label], 1u);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint16_t best = 0, sbest = 0, ib = 0, isb = 0, sum = 0;
+            uint32_t n = 0;
+            uint16_t* row = p.rows ? p.rows + (size_t)read * pitch : nullptr;
+            if (row) for (int i = 0; i < pitch; i++) row[i] = 0;
+            for (uint32_t t = 0; t < p.n_targets; t++) {
+                const uint16_t h = (uint16_t)hist[t];
+                hist[t] = 0;
+                if (!h) continue;
+                if (h > best) { sbest = best; isb = ib; best = h; ib = (uint16_t)(t + 1); }
+                else if (h > sbest) { sbest = h; isb = (uint16_t)(t + 1); }
+                sum = (uint16_t)(sum + h);
+                if (row && n < (uint32_t)p.row_pairs) { row[1 + 2 * n] = (uint16_t)t; row[2 + 2 * n] = h; }
+                n++;
+            }
+            if (row) { row[0] = (uint16_t)n; if (n > (uint32_t)p.row_pairs) atomicAdd(&p.counters[COUNTER_TRUNC], 1u); }
+            if (p.final5) {
+                uint16_t* f = p.final5 + (size_t)read * 5;
+                f[0] = sum; f[1] = ib; f[2] = best; f[3] = isb; f[4] = sbest;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// mergeKernel + resultKernel (src/CuClarkDB.cu:1321-1471) for n_parts shards:
+// n_parts-way merge of ascending sparse rows, summing equal targets, with the
+// top-2 scan folded in. One thread per read.
+__global__ void k_merge_rows(const uint16_t* __restrict__ parts, int n_parts, uint32_t n_reads, int row_pairs,
+                             uint16_t* rows_out, uint16_t* final5, uint32_t* counters) {
+    const uint32_t read = blockIdx.x * blockDim.x + threadIdx.x;
+    if (read >= n_reads) return;
+    const int pitch = 2 * row_pairs + 2;
+    const size_t part_stride = (size_t)n_reads * pitch;
+    int idx[16];
+    for (int g = 0; g < n_parts; g++) idx[g] = 0;
+    uint16_t best = 0, sbest = 0, ib = 0, isb = 0, sum = 0;
+    uint32_t n = 0;
+    uint16_t* out = rows_out ? rows_out + (size_t)read * pitch : nullptr;
+    for (;;) {
+        uint32_t tmin = 0x10000u;
+        for (int g = 0; g < n_parts; g++) {
+            const uint16_t* r = parts + g * part_stride + (size_t)read * pitch;
+            const int cnt = min((int)r[0], row_pairs);
+            if (idx[g] < cnt) tmin = min(tmin, (uint32_t)r[1 + 2 * idx[g]]);
+        }
+        if (tmin == 0x10000u) break;
+        uint16_t h = 0;
+        for (int g = 0; g < n_parts; g++) {
+            const uint16_t* r = parts + g * part_stride + (size_t)read * pitch;
+            const int cnt = min((int)r[0], row_pairs);
+            if (idx[g] < cnt && r[1 + 2 * idx[g]] == tmin) { h = (uint16_t)(h + r[2 + 2 * idx[g]]); idx[g]++; }
+        }
+        if (h > best) { sbest = best; isb = ib; best = h; ib = (uint16_t)(tmin + 1); }
+        else if (h > sbest) { sbest = h; isb = (uint16_t)(tmin + 1); }
+        sum = (uint16_t)(sum + h);
+        if (out && n < (uint32_t)row_pairs) { out[1 + 2 * n] = (uint16_t)tmin; out[2 + 2 * n] = h; }
+        n++;
+    }
+    if (out) {
+        out[0] = (uint16_t)n;
+        for (uint32_t i = 1 + 2 * min(n, (uint32_t)row_pairs); i < (uint32_t)pitch; i++) out[i] = 0;
+        if (n > (uint32_t)row_pairs) atomicAdd(&counters[COUNTER_TRUNC], 1u);
+    }
+    if (final5) {
+        uint16_t* f = final5 + (size_t)read * 5;
+        f[0] = sum; f[1] = ib; f[2] = best; f[3] = isb; f[4] = sbest;
+    }
+}
+
+// ---- synthetic reads, packed (device twin of synth.read_codes + oracle pack) ----
+__global__ void k_synth_reads(uint32_t seed, uint32_t genome_seed, uint32_t n_targets, uint64_t genome_len,
+                              uint64_t first_read, uint32_t n_reads, int read_len, int pct_random, int sub_per_10k,
+                              uint32_t* reads_ptr, uint16_t* cont) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t per_read = 1 + (read_len + 7) / 8;
+    if (r == 0) reads_ptr[n_reads] = n_reads * per_read;
+    if (r >= n_reads) return;
+    const uint64_t i = first_read + r;
+    const uint64_t h1 = synth::key(synth::TAG_READ, seed, i, 0), h2 = synth::key(synth::TAG_READ, seed, i, 1);
+    const bool is_random = (h1 % 100) < (uint64_t)pct_random;
+    const uint32_t target = (uint32_t)((h1 >> 8) % n_targets);
+    const bool is_rc = (h1 >> 40) & 1;
+    const uint64_t pos = h2 % (genome_len - read_len + 1);
+    uint16_t* c = cont + (size_t)r * per_read;
+    reads_ptr[r] = r * per_read;
+    c[0] = (uint16_t)read_len;
+    uint32_t word = 0, fill = 0, ci = 1;
+    for (int j = 0; j < read_len; j++) {
+        uint32_t code;
+        if (is_random) {
+            code = (uint32_t)(synth::key(synth::TAG_RBASE, seed, i, (uint64_t)(j >> 5)) >> (2 * (j & 31))) & 3u;
+        } else if (is_rc) {
+            code = 3u - synth::genome_base(genome_seed, target, pos + (read_len - 1 - j));
+        } else {
+            code = synth::genome_base(genome_seed, target, pos + j);
+        }
+        if (sub_per_10k) {
+            const uint64_t sh = synth::key(synth::TAG_SUB, seed, i, (uint64_t)j);
+            if ((sh % 10000) < (uint64_t)sub_per_10k) code = (code + 1 + (uint32_t)((sh >> 20) % 3)) & 3u;
+        }
+        word = (word << 2) | (3u - code);        // packed code is the complement code
+        if (++fill == 8) { c[ci++] = (uint16_t)word; word = 0; fill = 0; }
+    }
+    if (fill) c[ci] = (uint16_t)(word << (2 * (8 - fill)));
+}
+
+// ---- random-sector gather: the roofline denominator ----------------------------
+template <int BYTES, int ILP>
+__global__ void __launch_bounds__(256) k_gather(const uint4* __restrict__ base, uint64_t n_units, uint64_t n_probes,
+                                                uint64_t salt, uint32_t* sink) {
+    const uint64_t tid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    const uint64_t stride = gridDim.x * (uint64_t)blockDim.x;
+    uint32_t acc = 0;
+    // n_probes is rounded up to a multiple of stride*ILP by the host, so every
+    // load below is unconditional and all ILP of them are in flight together
+    for (uint64_t i = tid; i < n_probes; i += stride * ILP) {
+        uint4 v[ILP][BYTES / 16];
+        const uint4* ptr[ILP];
+#pragma unroll
+        for (int j = 0; j < ILP; j++) {
+            const uint64_t h = synth::mix64((i + j * stride) ^ salt);
+            ptr[j] = base + __umul64hi(h, n_units) * (BYTES / 16);      // uniform in [0, n_units)
+        }
+#pragma unroll
+        for (int j = 0; j < ILP; j++) {
+            if (BYTES == 32) {
+                asm("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                    : "=r"(v[j][0].x), "=r"(v[j][0].y), "=r"(v[j][0].z), "=r"(v[j][0].w),
+                      "=r"(v[j][1].x), "=r"(v[j][1].y), "=r"(v[j][1].z), "=r"(v[j][1].w)
+                    : "l"(ptr[j]));
+            } else {
+#pragma unroll
+                for (int q = 0; q < BYTES / 16; q++)
+                    asm("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                        : "=r"(v[j][q].x), "=r"(v[j][q].y), "=r"(v[j][q].z), "=r"(v[j][q].w)
+                        : "l"(ptr[j] + q));
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < ILP; j++)
+#pragma unroll
+            for (int q = 0; q < BYTES / 16; q++) acc ^= v[j][q].x ^ v[j][q].y ^ v[j][q].z ^ v[j][q].w;
+    }
+    if (acc == 0x12345678u) *sink = acc;      // keep the loads alive
+}
+
+template <int BYTES>
+void gather_dispatch(int ilp, int blocks, const uint4* base, uint64_t n_units, uint64_t n_probes, uint64_t salt,
+                     uint32_t* sink, cudaStream_t st) {
+    switch (ilp) {
+        case 1: k_gather<BYTES, 1><<<blocks, 256, 0, st>>>(base, n_units, n_probes, salt, sink); break;
+        case 2: k_gather<BYTES, 2><<<blocks, 256, 0, st>>>(base, n_units, n_probes, salt, sink); break;
+        case 8: k_gather<BYTES, 8><<<blocks, 256, 0, st>>>(base, n_units, n_probes, salt, sink); break;
+        default: k_gather<BYTES, 4><<<blocks, 256, 0, st>>>(base, n_units, n_probes, salt, sink); break;
+    }
+}
+
+}  // namespace
+
+template <typename K>
+static int blocks_per_sm(K kernel) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, WARPS_PER_BLOCK * 32, 0) != cudaSuccess || n < 1) n = 1;
+    return n;
+}
+
+int classify_launch(cuclark_db* db, const Scratch& sc, const uint32_t* d_ptr, const uint16_t* d_cont, size_t n_reads,
+                    uint16_t* d_final, uint16_t* d_rows, cudaStream_t st) {
+    if (!db->d_table) { set_error("no database loaded"); return CUCLARK_ERR_STATE; }
+    if (n_reads > 0xFFFFFFF0ull) { set_error("too many reads in one call"); return CUCLARK_ERR_ARG; }
+    if (db->row_pairs > MAX_ROW_PAIRS) { set_error("row_pairs > %d", MAX_ROW_PAIRS); return CUCLARK_ERR_ARG; }
+    ClassifyParams p;
+    p.t = db->view;
+    p.reads_ptr = d_ptr; p.cont = d_cont; p.n_reads = (uint32_t)n_reads;
+    p.final5 = d_final; p.rows = d_rows; p.row_pairs = db->row_pairs;
+    p.n_targets = (uint32_t)db->cfg.n_targets;
+    p.counters = sc.d_counters; p.dense_list = sc.d_dense_list; p.dense_cap = sc.dense_cap;
+    CK(cudaMemsetAsync(sc.d_counters, 0, N_COUNTERS * sizeof(uint32_t), st));
+    if (n_reads == 0) return CUCLARK_OK;
+    const bool narrow = db->view.layout == LAYOUT_NARROW;
+    // persistent grid: SM count x resident blocks per SM (one wave), capped by the work
+    const int variant = (narrow ? 0 : 2) + (d_rows ? 1 : 0);
+    if (!db->classify_blocks_per_sm[variant]) {
+        int n;
+        if (d_rows) n = narrow ? blocks_per_sm(k_classify<LAYOUT_NARROW, true>) : blocks_per_sm(k_classify<LAYOUT_WIDE, true>);
+        else n = narrow ? blocks_per_sm(k_classify<LAYOUT_NARROW, false>) : blocks_per_sm(k_classify<LAYOUT_WIDE, false>);
+        db->classify_blocks_per_sm[variant] = n;
+    }
+    const int blocks_needed = (int)((n_reads + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+    const int blocks = std::min(blocks_needed, db->sm_count * db->classify_blocks_per_sm[variant]);
+    if (d_rows) {
+        if (narrow) k_classify<LAYOUT_NARROW, true><<<blocks, WARPS_PER_BLOCK * 32, 0, st>>>(p);
+        else k_classify<LAYOUT_WIDE, true><<<blocks, WARPS_PER_BLOCK * 32, 0, st>>>(p);
+    } else {
+        if (narrow) k_classify<LAYOUT_NARROW, false><<<blocks, WARPS_PER_BLOCK * 32, 0, st>>>(p);
+        else k_classify<LAYOUT_WIDE, false><<<blocks, WARPS_PER_BLOCK * 32, 0, st>>>(p);
+    }
+    CK(cudaGetLastError());
+    // exact fallback; exits at once when the list is empty. Its histogram
+    // scratch is shared, so dense kernels are chained across streams.
+    CK(cudaStreamWaitEvent(st, db->dense_chain, 0));
+    if (narrow) k_classify_dense<LAYOUT_NARROW><<<db->dense_blocks, 256, 0, st>>>(p, db->d_dense_hist);
+    else k_classify_dense<LAYOUT_WIDE><<<db->dense_blocks, 256, 0, st>>>(p, db->d_dense_hist);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(db->dense_chain, st));
+    return CUCLARK_OK;
+}
+
+int merge_rows_launch(cuclark_db* db, const uint16_t* d_parts, int n_parts, size_t n_reads, uint16_t* d_rows_out,
+                      uint16_t* d_final, cudaStream_t st) {
+    if (n_parts < 1 || n_parts > 16) { set_error("n_parts must be 1..16"); return CUCLARK_ERR_ARG; }
+    if (n_reads == 0) return CUCLARK_OK;
+    k_merge_rows<<<(unsigned)((n_reads + 255) / 256), 256, 0, st>>>(d_parts, n_parts, (uint32_t)n_reads, db->row_pairs,
+                                                                   d_rows_out, d_final, db->scratch.d_counters);
+    CK(cudaGetLastError());
+    return CUCLARK_OK;
+}
+
+int synth_reads_launch(uint32_t seed, uint32_t genome_seed, uint32_t n_targets, uint64_t genome_len,
+                       uint64_t first_read, size_t n_reads, int read_len, int pct_random, int sub_per_10k,
+                       uint32_t* d_ptr, uint16_t* d_cont, cudaStream_t st) {
+    if (read_len < 1 || read_len > 65535 || genome_len < (uint64_t)read_len) { set_error("bad read_len"); return CUCLARK_ERR_ARG; }
+    const uint64_t per_read = 1 + (read_len + 7) / 8;
+    if (n_reads * per_read > 0xFFFFFFFFull) { set_error("batch exceeds 2^32 containers"); return CUCLARK_ERR_ARG; }
+    k_synth_reads<<<(unsigned)((n_reads + 256) / 256), 256, 0, st>>>(seed, genome_seed, n_targets, genome_len, first_read,
+                                                                     (uint32_t)n_reads, read_len, pct_random, sub_per_10k,
+                                                                     d_ptr, d_cont);
+    CK(cudaGetLastError());
+    return CUCLARK_OK;
+}
+
+int gather_bench_launch(cuclark_db* db, uint64_t n_probes, int bytes_per_probe, int ilp, int iters, double* ms_out) {
+    if (!db->d_table) { set_error("no database loaded"); return CUCLARK_ERR_STATE; }
+    if (bytes_per_probe != 32 && bytes_per_probe != 64 && bytes_per_probe != 128) { set_error("bytes_per_probe must be 32, 64 or 128"); return CUCLARK_ERR_ARG; }
+    const uint64_t n_units = db->view.n_local * 32 / bytes_per_probe;
+    if (n_units == 0) { set_error("table too small"); return CUCLARK_ERR_ARG; }
+    const int blocks = db->sm_count * 8;
+    const uint64_t quantum = (uint64_t)blocks * 256 * (ilp == 1 || ilp == 2 || ilp == 8 ? ilp : 4);
+    n_probes = (n_probes + quantum - 1) / quantum * quantum;
+    cudaStream_t st = db->stream;
+    for (int it = -1; it < iters; it++) {
+        if (it == 0) CK(cudaEventRecord(db->ev0, st));
+        const uint64_t salt = 0x5bd1e995ull * (uint64_t)(it + 2);
+        if (bytes_per_probe == 32) gather_dispatch<32>(ilp, blocks, db->d_table, n_units, n_probes, salt, db->scratch.d_counters + 6, st);
+        else if (bytes_per_probe == 64) gather_dispatch<64>(ilp, blocks, db->d_table, n_units, n_probes, salt, db->scratch.d_counters + 6, st);
+        else gather_dispatch<128>(ilp, blocks, db->d_table, n_units, n_probes, salt, db->scratch.d_counters + 6, st);
+        CK(cudaGetLastError());
+    }
+    CK(cudaEventRecord(db->ev1, st));
+    CK(cudaEventSynchronize(db->ev1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, db->ev0, db->ev1));
+    *ms_out = ms / iters;
+    return CUCLARK_OK;
+}
+
+}  // namespace cuclark

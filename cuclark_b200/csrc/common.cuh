@@ -1,0 +1,160 @@
+// cuclark_b200 — shared device/host definitions.
+//
+// Device table layout ("sector buckets"), designed for one 32-byte HBM sector
+// per probe. The reference keeps three arrays (bucket pointers, keys, labels;
+// src/CuClarkDB.cu:1268-1313) and touches >= 3 sectors per lookup; here every
+// canonical k-mer c has exactly one home bucket of 32 bytes:
+//
+//     b   = c mod M            (M = number of device buckets, our own modulus)
+//     key = c div M            (exact quotient: no lossy fingerprint)
+//
+//   NARROW (key fits 32 bit, i.e. M > 4^k / (2^32-1)):
+//     word 0..4   key[0..4]            (0xFFFFFFFF = empty)
+//     word 5      label[0] | label[1] << 16
+//     word 6      label[2] | label[3] << 16
+//     word 7      label[4] | meta << 16
+//   WIDE (any k <= 32, any M; used for small tables):
+//     word 0..5   key[0..2] as uint64  (all-ones = empty)
+//     word 6      label[0] | label[1] << 16
+//     word 7      label[2] | meta << 16
+//
+//   meta (16 bit): bits 0..1  maxdisp  = how far entries homed HERE spilled (0..3)
+//                  bits 2+2i..3+2i     disp[i] = distance of slot i from ITS home
+//   A bucket that is full spills into the next 1..3 buckets (same shard). A
+//   lookup reads its home sector, and only if maxdisp > 0 and the key was not
+//   found does it read home+1..home+maxdisp. With a mean load of ~2.5 entries
+//   per 5-slot bucket ~4% of buckets spill, so the expected cost is ~1.04
+//   sectors per lookup for hits and misses alike.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+namespace cuclark {
+
+constexpr int LAYOUT_NARROW = 1;
+constexpr int LAYOUT_WIDE = 2;
+constexpr int NARROW_SLOTS = 5;
+constexpr int WIDE_SLOTS = 3;
+constexpr int MAX_DISP = 3;
+constexpr uint32_t NO_LABEL = 0xFFFFFFFFu;
+
+struct TableView {
+    const uint4* buckets;   // 2 x uint4 per bucket, 32-byte aligned
+    uint64_t M;             // global number of buckets (the modulus)
+    uint64_t magic;         // floor(2^64 / M)
+    uint64_t lo;            // this shard holds home buckets [lo, lo+n_local)
+    uint64_t n_local;
+    int layout;
+    int k;
+};
+
+// ---- k-mer arithmetic -------------------------------------------------------
+// Reverse complement of a 2k-bit code, as src/CuClarkDB.cu:1255-1263 defines it
+// (reverse the 2-bit groups, complement, shift down): brev reverses all 64
+// bits, the swap puts each pair back in order.
+__host__ __device__ __forceinline__ uint64_t revcomp2(uint64_t x, int k) {
+#ifdef __CUDA_ARCH__
+    uint64_t r = __brevll(x);
+#else
+    uint64_t r = x;
+    r = ((r >> 1) & 0x5555555555555555ull) | ((r & 0x5555555555555555ull) << 1);
+    r = ((r >> 2) & 0x3333333333333333ull) | ((r & 0x3333333333333333ull) << 2);
+    r = ((r >> 4) & 0x0F0F0F0F0F0F0F0Full) | ((r & 0x0F0F0F0F0F0F0F0Full) << 4);
+    r = ((r >> 8) & 0x00FF00FF00FF00FFull) | ((r & 0x00FF00FF00FF00FFull) << 8);
+    r = ((r >> 16) & 0x0000FFFF0000FFFFull) | ((r & 0x0000FFFF0000FFFFull) << 16);
+    r = (r >> 32) | (r << 32);
+#endif
+    r = ((r >> 1) & 0x5555555555555555ull) | ((r & 0x5555555555555555ull) << 1);
+    return (~r) >> (64 - 2 * k);
+}
+
+__host__ __device__ __forceinline__ uint64_t canonical(uint64_t x, int k) {
+    uint64_t r = revcomp2(x, k);
+    return x < r ? x : r;
+}
+
+// c = q*M + r with a precomputed floor(2^64/M); c < 2^64, exact after one fix-up
+// (the estimate is q or q-1 because c * (2^64 mod M) / M < 2^64).
+__device__ __forceinline__ void divmod_M(uint64_t c, uint64_t M, uint64_t magic, uint64_t& q, uint64_t& r) {
+    q = __umul64hi(c, magic);
+    r = c - q * M;
+    if (r >= M) { r -= M; q++; }
+}
+
+// ---- 32-byte probe ------------------------------------------------------------
+struct Sector { uint32_t w[8]; };
+
+__device__ __forceinline__ Sector load_sector(const uint4* p) {
+    Sector s;
+    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(s.w[0]), "=r"(s.w[1]), "=r"(s.w[2]), "=r"(s.w[3]),
+                   "=r"(s.w[4]), "=r"(s.w[5]), "=r"(s.w[6]), "=r"(s.w[7])
+                 : "l"(p));
+    return s;
+}
+
+// Match `key` among the slots of a sector whose displacement equals d.
+// Returns the label or NO_LABEL. Empty slots hold an all-ones key, which no
+// valid quotient equals (M is chosen so that quotients stay below it).
+template <int LAYOUT>
+__device__ __forceinline__ uint32_t match_sector(const Sector& s, uint64_t key, uint32_t d) {
+    const uint32_t meta = s.w[7] >> 16;
+    uint32_t label = NO_LABEL;
+    if (LAYOUT == LAYOUT_NARROW) {
+        const uint32_t k32 = (uint32_t)key;
+#pragma unroll
+        for (int i = 0; i < NARROW_SLOTS; i++) {
+            const uint32_t disp = (meta >> (2 + 2 * i)) & 3u;
+            const uint32_t lw = s.w[5 + (i >> 1)];
+            const uint32_t l = (i & 1) ? (lw >> 16) : (lw & 0xFFFFu);
+            if (s.w[i] == k32 && disp == d) label = l;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < WIDE_SLOTS; i++) {
+            const uint64_t kk = (uint64_t)s.w[2 * i] | ((uint64_t)s.w[2 * i + 1] << 32);
+            const uint32_t disp = (meta >> (2 + 2 * i)) & 3u;
+            const uint32_t lw = s.w[6 + (i >> 1)];
+            const uint32_t l = (i & 1) ? (lw >> 16) : (lw & 0xFFFFu);
+            if (kk == key && disp == d) label = l;
+        }
+    }
+    return label;
+}
+
+__device__ __forceinline__ uint32_t sector_maxdisp(const Sector& s) { return (s.w[7] >> 16) & 3u; }
+
+// Full lookup of one canonical k-mer (used by the slow paths; the hot kernel
+// inlines the same steps so that it can batch the home-sector loads).
+template <int LAYOUT>
+__device__ __forceinline__ uint32_t table_lookup(const TableView& t, uint64_t c) {
+    uint64_t q, b;
+    divmod_M(c, t.M, t.magic, q, b);
+    uint64_t lb = b - t.lo;
+    if (lb >= t.n_local) return NO_LABEL;           // other shard (b < lo wraps around)
+    Sector s = load_sector(t.buckets + 2 * lb);
+    uint32_t label = match_sector<LAYOUT>(s, q, 0);
+    uint32_t md = sector_maxdisp(s);
+    for (uint32_t d = 1; label == NO_LABEL && d <= md; d++) {
+        uint64_t nb = lb + d;
+        if (nb >= t.n_local) nb -= t.n_local;
+        Sector s2 = load_sector(t.buckets + 2 * nb);
+        label = match_sector<LAYOUT>(s2, q, d);
+    }
+    return label;
+}
+
+// ---- error handling -------------------------------------------------------------
+void set_error(const char* fmt, ...);
+#define CK(call)                                                                       \
+    do {                                                                               \
+        cudaError_t e_ = (call);                                                       \
+        if (e_ != cudaSuccess) {                                                       \
+            cuclark::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                               __FILE__, __LINE__);                                    \
+            return CUCLARK_ERR_CUDA;                                                   \
+        }                                                                              \
+    } while (0)
+
+}  // namespace cuclark

@@ -1,0 +1,88 @@
+// cuclark_b200 — internal handle and cross-TU prototypes (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <vector>
+
+#include "../../include/cuclark_b200.h"
+#include "common.cuh"
+
+namespace cuclark {
+
+constexpr int COUNTER_DENSE = 0;       // reads routed to the dense fallback
+constexpr int COUNTER_TRUNC = 1;       // rows with more than row_pairs targets
+constexpr int COUNTER_LOOKUPS = 2;     // uint64 at [2],[3]
+constexpr int N_COUNTERS = 8;
+
+// Per-call scratch: counters and the list of reads for the dense fallback.
+struct Scratch {
+    uint32_t* d_counters = nullptr;    // N_COUNTERS
+    uint32_t* d_dense_list = nullptr;
+    uint32_t dense_cap = 0;
+};
+
+struct Batch {
+    Scratch scratch;
+    uint32_t* h_counters = nullptr;    // pinned copy of the counters
+    uint32_t* h_ptr = nullptr;         // pinned
+    uint16_t* h_cont = nullptr;
+    uint16_t* h_final = nullptr;
+    uint16_t* h_rows = nullptr;
+    uint32_t* d_ptr = nullptr;
+    uint16_t* d_cont = nullptr;
+    uint16_t* d_final = nullptr;
+    uint16_t* d_rows = nullptr;
+    size_t n_reads = 0, n_cont = 0;
+    bool ready = false, queried = false;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+};
+
+}  // namespace cuclark
+
+struct cuclark_db {
+    cuclark_config cfg;
+    int row_pairs;
+    int key_bytes;
+    // device table
+    uint4* d_table = nullptr;
+    cuclark::TableView view{};
+    uint64_t n_entries = 0, n_spilled = 0, n_spill_buckets = 0;
+    // classify scratch (one-shot calls; batches carry their own)
+    cuclark::Scratch scratch;
+    uint32_t* d_dense_hist = nullptr;  // dense_blocks * n_targets, shared: dense kernels are
+    cudaEvent_t dense_chain = nullptr; //   serialised across streams through this event
+    int dense_blocks = 0;
+    int classify_blocks_per_sm[4] = {0, 0, 0, 0};
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;     // library-owned default stream
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // last-call stats
+    uint64_t last_lookups = 0, last_dense = 0, last_trunc = 0;
+    double last_ms = 0;
+    // batches
+    std::vector<cuclark::Batch> batches;
+    size_t batch_max_reads = 0, batch_max_cont = 0;
+    bool batch_rows = false;
+};
+
+namespace cuclark {
+
+// table.cu
+int table_build_from_arrays(cuclark_db* db, const uint8_t* sz, const void* ky, const uint16_t* lb,
+                            uint64_t n_entries_file, int sfactor, const char* base_path);
+int table_build_synthetic(cuclark_db* db, uint32_t seed, uint32_t n_targets, uint64_t genome_len, int light_gap);
+void table_free(cuclark_db* db);
+
+// classify.cu
+int classify_launch(cuclark_db* db, const Scratch& sc, const uint32_t* d_ptr, const uint16_t* d_cont, size_t n_reads,
+                    uint16_t* d_final, uint16_t* d_rows, cudaStream_t st);
+int merge_rows_launch(cuclark_db* db, const uint16_t* d_parts, int n_parts, size_t n_reads, uint16_t* d_rows_out,
+                      uint16_t* d_final, cudaStream_t st);
+int synth_reads_launch(uint32_t seed, uint32_t genome_seed, uint32_t n_targets, uint64_t genome_len,
+                       uint64_t first_read, size_t n_reads, int read_len, int pct_random, int sub_per_10k,
+                       uint32_t* d_ptr, uint16_t* d_cont, cudaStream_t st);
+int gather_bench_launch(cuclark_db* db, uint64_t n_probes, int bytes_per_probe, int ilp, int iters, double* ms_out);
+
+}  // namespace cuclark

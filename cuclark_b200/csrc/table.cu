@@ -1,0 +1,556 @@
+// cuclark_b200 — device table construction ("re-bucketing").
+//
+// Replaces CuClarkDB::read / swapDbParts (reference src/CuClarkDB.cu:462-858):
+// instead of per-part prefix-sum pointers + key and label arrays copied as they
+// lie in the files, the (bucket r, quotient q, label) triples of <base>.sz/.ky/.lb
+// (format: src/hashTable_hh.hh:591-663) are turned back into canonical k-mers
+// c = q*HTSIZE + r and scattered ON THE DEVICE into 32-byte sector buckets
+// (layout in common.cuh). The whole table stays resident in HBM: no swap cycles,
+// no 32-bit bucket pointers.
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "internal.h"
+#include "synth.cuh"
+
+namespace cuclark {
+
+namespace {
+
+constexpr uint32_t ERR_OVF_LIST = 1, ERR_COUNTER = 2, ERR_NO_SLOT = 4;
+constexpr int CHUNK_THREADS = 1024;
+constexpr uint32_t CHUNK_BLOCKS = 16384;           // 16.7M reference buckets per chunk
+
+struct BuildCtx {
+    uint4* table;
+    uint32_t* cnt8;        // one byte per local bucket, packed 4 per word
+    uint64_t M, magic, lo, n_local, htsize;
+    uint64_t* ovf_c;       // k-mers that did not fit their home bucket
+    uint16_t* ovf_l;
+    uint32_t ovf_cap;
+    uint32_t* flags;       // [0] overflow count, [1] error bits
+    unsigned long long* inserted;   // entries homed in this shard
+};
+
+template <int LAYOUT>
+__device__ __forceinline__ void write_slot(uint4* table, uint64_t lb, uint32_t slot, uint64_t q, uint32_t label,
+                                           uint32_t d) {
+    uint32_t* w = reinterpret_cast<uint32_t*>(table + 2 * lb);
+    if (LAYOUT == LAYOUT_NARROW) {
+        w[slot] = (uint32_t)q;
+        atomicOr(&w[5 + (slot >> 1)], label << (16 * (slot & 1)));
+    } else {
+        reinterpret_cast<uint64_t*>(w)[slot] = q;
+        atomicOr(&w[6 + (slot >> 1)], label << (16 * (slot & 1)));
+    }
+    if (d) atomicOr(&w[7], d << (16 + 2 + 2 * slot));
+}
+
+__device__ __forceinline__ uint32_t claim_slot(const BuildCtx& x, uint64_t lb) {
+    const uint32_t sh = 8 * (uint32_t)(lb & 3);
+    const uint32_t old = (atomicAdd(&x.cnt8[lb >> 2], 1u << sh) >> sh) & 0xFFu;
+    if (old == 255u) atomicOr(&x.flags[1], ERR_COUNTER);
+    return old;
+}
+
+template <int LAYOUT>
+__device__ __forceinline__ bool insert_home(const BuildCtx& x, uint64_t c, uint32_t label) {
+    constexpr uint32_t SLOTS = LAYOUT == LAYOUT_NARROW ? NARROW_SLOTS : WIDE_SLOTS;
+    uint64_t q, b;
+    divmod_M(c, x.M, x.magic, q, b);
+    const uint64_t lb = b - x.lo;
+    if (lb >= x.n_local) return false;               // homed in another shard
+    const uint32_t slot = claim_slot(x, lb);
+    if (slot < SLOTS) {
+        write_slot<LAYOUT>(x.table, lb, slot, q, label, 0);
+    } else {
+        const uint32_t i = atomicAdd(&x.flags[0], 1u);
+        if (i < x.ovf_cap) { x.ovf_c[i] = c; x.ovf_l[i] = (uint16_t)label; }
+        else atomicOr(&x.flags[1], ERR_OVF_LIST);
+    }
+    return true;
+}
+
+__global__ void k_init_table(uint4* table, uint64_t n_local, int layout) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;   // one uint4 each
+    if (i >= 2 * n_local) return;
+    uint4 v;
+    if (layout == LAYOUT_NARROW) {
+        v = (i & 1) ? make_uint4(0xFFFFFFFFu, 0u, 0u, 0u) : make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+    } else {
+        v = (i & 1) ? make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u) : make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+    }
+    table[i] = v;
+}
+
+// One thread per reference bucket of the chunk; block-wide exclusive scan of
+// the bucket sizes gives each bucket its offset into the chunk's keys/labels.
+template <int LAYOUT>
+__global__ void __launch_bounds__(CHUNK_THREADS) k_insert_chunk(BuildCtx x, const uint8_t* __restrict__ sz,
+                                                                const uint8_t* __restrict__ keep,
+                                                                const uint64_t* __restrict__ coarse, uint64_t r0,
+                                                                uint32_t nb, const void* __restrict__ keys,
+                                                                const uint16_t* __restrict__ labels, int key_bytes) {
+    __shared__ uint32_t warp_sum[CHUNK_THREADS / 32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t r = blockIdx.x * CHUNK_THREADS + tid;
+    const uint32_t s = r < nb ? sz[r] : 0;
+    uint32_t incl = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) warp_sum[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t v = warp_sum[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t u = __shfl_up_sync(0xFFFFFFFFu, v, o);
+            if (lane >= o) v += u;
+        }
+        warp_sum[lane] = v;
+    }
+    __syncthreads();
+    const uint64_t off = coarse[blockIdx.x] + (wid ? warp_sum[wid - 1] : 0) + (incl - s);
+    if (s == 0 || (keep && !keep[r])) return;
+    unsigned long long mine = 0;
+    for (uint32_t i = 0; i < s; i++) {
+        uint64_t q;
+        if (key_bytes == 4) q = static_cast<const uint32_t*>(keys)[off + i];
+        else if (key_bytes == 2) q = static_cast<const uint16_t*>(keys)[off + i];
+        else q = static_cast<const uint64_t*>(keys)[off + i];
+        const uint64_t c = q * x.htsize + (r0 + r);
+        mine += insert_home<LAYOUT>(x, c, labels[off + i]);
+    }
+    if (mine) atomicAdd(x.inserted, mine);
+}
+
+// Entries whose home bucket was full go to the next 1..MAX_DISP buckets.
+template <int LAYOUT>
+__global__ void k_place_spills(BuildCtx x, uint32_t n) {
+    constexpr uint32_t SLOTS = LAYOUT == LAYOUT_NARROW ? NARROW_SLOTS : WIDE_SLOTS;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t c = x.ovf_c[i];
+    const uint32_t label = x.ovf_l[i];
+    uint64_t q, b;
+    divmod_M(c, x.M, x.magic, q, b);
+    const uint64_t lb = b - x.lo;
+    for (uint32_t d = 1; d <= (uint32_t)MAX_DISP; d++) {
+        uint64_t nb = lb + d;
+        if (nb >= x.n_local) nb -= x.n_local;
+        const uint32_t slot = claim_slot(x, nb);
+        if (slot >= SLOTS) continue;
+        write_slot<LAYOUT>(x.table, nb, slot, q, label, d);
+        // raise maxdisp (meta bits 0..1) of the HOME bucket to at least d
+        uint32_t* w7 = reinterpret_cast<uint32_t*>(x.table + 2 * lb) + 7;
+        uint32_t old = *w7;
+        while (((old >> 16) & 3u) < d) {
+            const uint32_t assumed = old;
+            old = atomicCAS(w7, assumed, (assumed & ~(3u << 16)) | (d << 16));
+            if (old == assumed) break;
+        }
+        return;
+    }
+    atomicOr(&x.flags[1], ERR_NO_SLOT);
+}
+
+__global__ void k_table_stats(const uint4* table, uint64_t n_local, unsigned long long* out) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    bool spill = false;
+    if (i < n_local) spill = ((table[2 * i + 1].w >> 16) & 3u) != 0;
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, spill);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(out, (unsigned long long)__popc(m));
+}
+
+// ---- synthetic database (bench.py) -------------------------------------------
+// Every overlapping k-mer of every target (full variant, src/CuCLARK_hh.hh:896-975).
+template <int LAYOUT>
+__global__ void k_synth_insert_full(BuildCtx x, uint32_t seed, uint32_t n_targets, uint64_t genome_len, int k,
+                                    uint64_t runs_per_target) {
+    constexpr int RUN = 64;
+    const uint64_t g = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (g >= runs_per_target * n_targets) return;
+    const uint32_t t = (uint32_t)(g / runs_per_target);
+    const uint64_t p0 = (g % runs_per_target) * RUN;
+    const uint64_t nk = genome_len - k + 1;
+    const uint64_t mask = (~0ull) >> (64 - 2 * k);
+    uint64_t R = 0, word = 0;
+    unsigned long long mine = 0;
+    for (uint64_t p = p0; p < p0 + RUN + k - 1 && p < genome_len; p++) {
+        if (p == p0 || (p & 31) == 0) word = synth::genome_word(seed, t, p >> 5);
+        const uint32_t code = (uint32_t)(word >> (2 * (p & 31))) & 3u;
+        R = ((R << 2) | (3u - code)) & mask;
+        if (p >= p0 + k - 1 && p - (k - 1) < nk) mine += insert_home<LAYOUT>(x, canonical(R, k), t);
+    }
+    if (mine) atomicAdd(x.inserted, mine);
+}
+
+// Every gap-th non-overlapping k-mer (light variant, src/CuCLARK_hh.hh:705-767).
+template <int LAYOUT>
+__global__ void k_synth_insert_light(BuildCtx x, uint32_t seed, uint32_t n_targets, uint64_t genome_len, int k,
+                                     int gap, uint64_t per_target) {
+    const uint64_t g = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (g >= per_target * n_targets) return;
+    const uint32_t t = (uint32_t)(g / per_target);
+    const uint64_t start = (g % per_target) * (uint64_t)gap * k;
+    uint64_t R = 0;
+    for (int j = 0; j < k; j++) R = (R << 2) | (3u - synth::genome_base(seed, t, start + j));
+    if (insert_home<LAYOUT>(x, canonical(R, k), t)) atomicAdd(x.inserted, 1ull);
+}
+
+// RemoveCommon (src/HashTableStorage_hh.hh:242-292) for the synthetic builder:
+// a k-mer inserted more than once is kept once if all copies carry the same
+// label and removed entirely otherwise. All copies share one home bucket.
+template <int LAYOUT>
+__global__ void k_dedupe(uint4* table, uint64_t n_local, unsigned long long* removed) {
+    constexpr int SLOTS = LAYOUT == LAYOUT_NARROW ? NARROW_SLOTS : WIDE_SLOTS;
+    constexpr int CAP = SLOTS * (MAX_DISP + 1);
+    const uint64_t lb = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (lb >= n_local) return;
+    uint32_t* home = reinterpret_cast<uint32_t*>(table + 2 * lb);
+    const uint32_t md = (home[7] >> 16) & 3u;
+    uint64_t keys[CAP];
+    uint32_t labels[CAP];
+    uint32_t where[CAP];   // d * 8 + slot
+    int n = 0;
+    for (uint32_t d = 0; d <= md; d++) {
+        uint64_t nb = lb + d;
+        if (nb >= n_local) nb -= n_local;
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(table + 2 * nb);
+        const uint32_t meta = w[7] >> 16;
+        for (int s = 0; s < SLOTS; s++) {
+            if (((meta >> (2 + 2 * s)) & 3u) != d) continue;
+            uint64_t kk;
+            uint32_t lw;
+            if (LAYOUT == LAYOUT_NARROW) {
+                if (w[s] == 0xFFFFFFFFu) continue;
+                kk = w[s];
+                lw = w[5 + (s >> 1)];
+            } else {
+                kk = reinterpret_cast<const uint64_t*>(w)[s];
+                if (kk == ~0ull) continue;
+                lw = w[6 + (s >> 1)];
+            }
+            keys[n] = kk;
+            labels[n] = (s & 1) ? (lw >> 16) : (lw & 0xFFFFu);
+            where[n] = d * 8 + s;
+            n++;
+        }
+    }
+    unsigned long long gone = 0;
+    for (int i = 0; i < n; i++) {
+        if (where[i] == 0xFFFFFFFFu) continue;
+        bool common = false, dup = false;
+        for (int j = i + 1; j < n; j++) {
+            if (where[j] == 0xFFFFFFFFu || keys[j] != keys[i]) continue;
+            dup = true;
+            if (labels[j] != labels[i]) common = true;
+        }
+        if (!dup) continue;
+        for (int j = i + (common ? 0 : 1); j < n; j++) {
+            if (where[j] == 0xFFFFFFFFu || keys[j] != keys[i]) continue;
+            const uint32_t d = where[j] >> 3, s = where[j] & 7;
+            uint64_t nb = lb + d;
+            if (nb >= n_local) nb -= n_local;
+            uint32_t* w = reinterpret_cast<uint32_t*>(table + 2 * nb);
+            if (LAYOUT == LAYOUT_NARROW) w[s] = 0xFFFFFFFFu;
+            else reinterpret_cast<uint64_t*>(w)[s] = ~0ull;
+            if (j != i) where[j] = 0xFFFFFFFFu;
+            gone++;
+        }
+        where[i] = 0xFFFFFFFFu;
+    }
+    if (gone) atomicAdd(removed, gone);
+}
+
+// ---- host side ------------------------------------------------------------------
+struct Geometry {
+    int layout;
+    uint64_t M, lo, n_local;
+};
+
+uint64_t pow4(int k) { return k >= 32 ? 0 : (1ull << (2 * k)); }   // 0 means 2^64
+
+Geometry choose_geometry(const cuclark_config& cfg, uint64_t n_entries, double grow) {
+    Geometry g;
+    const double narrow_load = cfg.bucket_load > 0 ? cfg.bucket_load : 2.6;
+    const double wide_load = cfg.bucket_load > 0 ? std::min(cfg.bucket_load, 2.0) : 1.5;
+    // quotient c / M must stay below 2^32-1 in the narrow layout
+    uint64_t m_min_narrow = 0;
+    bool narrow_possible = cfg.k < 32;
+    if (narrow_possible) m_min_narrow = pow4(cfg.k) / 0xFFFFFFFFull + 2;
+    uint64_t m_narrow = (uint64_t)((double)n_entries / narrow_load * grow) + 64;
+    uint64_t m_wide = (uint64_t)((double)n_entries / wide_load * grow) + 64;
+    int layout = cfg.layout;
+    if (layout == 0) {
+        if (!narrow_possible) layout = LAYOUT_WIDE;
+        else {
+            const uint64_t need = std::max(m_narrow, m_min_narrow);
+            const uint64_t small = (256ull << 20) / 32;
+            layout = (need <= small || (double)need <= 1.25 * (double)m_wide) ? LAYOUT_NARROW : LAYOUT_WIDE;
+        }
+    }
+    if (layout == LAYOUT_NARROW && !narrow_possible) layout = LAYOUT_WIDE;
+    g.layout = layout;
+    g.M = layout == LAYOUT_NARROW ? std::max(m_narrow, m_min_narrow) : m_wide;
+    g.M |= 1ull;
+    const uint64_t G = cfg.shard_count > 1 ? cfg.shard_count : 1, i = cfg.shard_count > 1 ? cfg.shard_index : 0;
+    g.lo = (uint64_t)((__uint128_t)g.M * i / G);
+    const uint64_t hi = (uint64_t)((__uint128_t)g.M * (i + 1) / G);
+    g.n_local = hi - g.lo;
+    return g;
+}
+
+struct BuildBuffers {
+    uint4* table = nullptr;
+    uint32_t* cnt8 = nullptr;
+    uint64_t* ovf_c = nullptr;
+    uint16_t* ovf_l = nullptr;
+    uint32_t* flags = nullptr;
+    unsigned long long* counters = nullptr;   // [0] inserted, [1] spill buckets, [2] removed
+    void free_temp() {
+        cudaFree(cnt8); cudaFree(ovf_c); cudaFree(ovf_l); cudaFree(flags); cudaFree(counters);
+        cnt8 = nullptr; ovf_c = nullptr; ovf_l = nullptr; flags = nullptr; counters = nullptr;
+    }
+    void free_all() { free_temp(); cudaFree(table); table = nullptr; }
+};
+
+int alloc_build(const Geometry& g, uint64_t n_expected, BuildBuffers& b, BuildCtx& x, uint64_t htsize) {
+    const uint64_t G = 1;
+    (void)G;
+    uint64_t ovf_cap64 = n_expected / 6 + (1u << 16);
+    if (ovf_cap64 > 0xFFFFFF00ull) ovf_cap64 = 0xFFFFFF00ull;
+    if (cudaMalloc(&b.table, g.n_local * 32) != cudaSuccess) { cudaGetLastError(); set_error("cudaMalloc of %.2f GB table failed", g.n_local * 32 / 1e9); return CUCLARK_ERR_NOMEM; }
+    CK(cudaMalloc(&b.cnt8, (g.n_local / 4 + 1) * 4));
+    CK(cudaMalloc(&b.ovf_c, ovf_cap64 * 8));
+    CK(cudaMalloc(&b.ovf_l, ovf_cap64 * 2));
+    CK(cudaMalloc(&b.flags, 16));
+    CK(cudaMalloc(&b.counters, 32));
+    CK(cudaMemset(b.cnt8, 0, (g.n_local / 4 + 1) * 4));
+    CK(cudaMemset(b.flags, 0, 16));
+    CK(cudaMemset(b.counters, 0, 32));
+    const uint64_t n4 = 2 * g.n_local;
+    k_init_table<<<(unsigned)((n4 + 255) / 256), 256>>>(b.table, g.n_local, g.layout);
+    CK(cudaGetLastError());
+    x.table = b.table; x.cnt8 = b.cnt8; x.M = g.M; x.magic = (uint64_t)((((__uint128_t)1) << 64) / g.M);
+    x.lo = g.lo; x.n_local = g.n_local; x.htsize = htsize;
+    x.ovf_c = b.ovf_c; x.ovf_l = b.ovf_l; x.ovf_cap = (uint32_t)ovf_cap64; x.flags = b.flags;
+    x.inserted = b.counters;
+    return CUCLARK_OK;
+}
+
+// spills, stats, error check; returns CUCLARK_ERR_BUILD if the geometry was too tight
+int finish_build(cuclark_db* db, const Geometry& g, BuildBuffers& b, BuildCtx& x, bool dedupe) {
+    uint32_t flags[2];
+    CK(cudaMemcpy(flags, b.flags, 8, cudaMemcpyDeviceToHost));
+    if (flags[1]) { set_error("table build: bucket counter/overflow-list exhausted (flags %u)", flags[1]); return CUCLARK_ERR_BUILD; }
+    const uint32_t n_ovf = flags[0];
+    if (n_ovf) {
+        if (g.layout == LAYOUT_NARROW) k_place_spills<LAYOUT_NARROW><<<(n_ovf + 255) / 256, 256>>>(x, n_ovf);
+        else k_place_spills<LAYOUT_WIDE><<<(n_ovf + 255) / 256, 256>>>(x, n_ovf);
+        CK(cudaGetLastError());
+    }
+    if (dedupe) {
+        const unsigned blocks = (unsigned)((g.n_local + 255) / 256);
+        if (g.layout == LAYOUT_NARROW) k_dedupe<LAYOUT_NARROW><<<blocks, 256>>>(b.table, g.n_local, b.counters + 2);
+        else k_dedupe<LAYOUT_WIDE><<<blocks, 256>>>(b.table, g.n_local, b.counters + 2);
+        CK(cudaGetLastError());
+    }
+    k_table_stats<<<(unsigned)((g.n_local + 255) / 256), 256>>>(b.table, g.n_local, b.counters + 1);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(flags, b.flags, 8, cudaMemcpyDeviceToHost));
+    if (flags[1]) { set_error("table build: no free slot within %d buckets of home (flags %u)", MAX_DISP, flags[1]); return CUCLARK_ERR_BUILD; }
+    unsigned long long counters[3];
+    CK(cudaMemcpy(counters, b.counters, 24, cudaMemcpyDeviceToHost));
+    db->n_entries = counters[0] - counters[2];
+    db->n_spilled = n_ovf;
+    db->n_spill_buckets = counters[1];
+    db->d_table = b.table;
+    db->view.buckets = b.table;
+    db->view.M = g.M;
+    db->view.magic = x.magic;
+    db->view.lo = g.lo;
+    db->view.n_local = g.n_local;
+    db->view.layout = g.layout;
+    db->view.k = db->cfg.k;
+    b.free_temp();
+    return CUCLARK_OK;
+}
+
+}  // namespace
+
+void table_free(cuclark_db* db) {
+    if (db->d_table) cudaFree(db->d_table);
+    db->d_table = nullptr;
+    db->view = TableView{};
+    db->n_entries = db->n_spilled = db->n_spill_buckets = 0;
+}
+
+int table_build_from_arrays(cuclark_db* db, const uint8_t* sz_in, const void* ky, const uint16_t* lb,
+                            uint64_t n_entries_file, int sfactor, const char* base_path) {
+    const uint64_t H = db->cfg.htsize;
+    const int kb = db->key_bytes;
+    FILE *f_ky = nullptr, *f_lb = nullptr;
+    std::vector<uint8_t> sz_file;
+    const uint8_t* sz = sz_in;
+    if (base_path) {
+        std::string b(base_path);
+        FILE* f_sz = fopen((b + ".sz").c_str(), "rb");
+        if (!f_sz) { set_error("Failed to open %s.sz", base_path); return CUCLARK_ERR_IO; }
+        f_ky = fopen((b + ".ky").c_str(), "rb");
+        if (!f_ky) { fclose(f_sz); set_error("Failed to open %s.ky", base_path); return CUCLARK_ERR_IO; }
+        f_lb = fopen((b + ".lb").c_str(), "rb");
+        if (!f_lb) { fclose(f_sz); fclose(f_ky); set_error("Failed to open %s.lb", base_path); return CUCLARK_ERR_IO; }
+        sz_file.resize(H);
+        const size_t got = fread(sz_file.data(), 1, H, f_sz);
+        fclose(f_sz);
+        if (got != H) { fclose(f_ky); fclose(f_lb); set_error("%s.sz is short (%zu of %llu bytes)", base_path, got, (unsigned long long)H); return CUCLARK_ERR_IO; }
+        sz = sz_file.data();
+    }
+    struct Closer { FILE *a, *b; ~Closer() { if (a) fclose(a); if (b) fclose(b); } } closer{f_ky, f_lb};
+
+    // one host pass over the bucket sizes: -s sampling (src/CuClarkDB.cu:511-524),
+    // kept-entry count, and the file offset of every 1024th bucket
+    const uint64_t n_blocks = (H + CHUNK_THREADS - 1) / CHUNK_THREADS;
+    std::vector<uint64_t> coarse(n_blocks + 1);
+    std::vector<uint8_t> keep;
+    if (sfactor > 1) keep.assign(H, 0);
+    uint64_t total = 0, kept = 0, nonzero = 0;
+    for (uint64_t r = 0; r < H; r++) {
+        if ((r % CHUNK_THREADS) == 0) coarse[r / CHUNK_THREADS] = total;
+        const uint32_t s = sz[r];
+        if (!s) continue;
+        nonzero++;
+        total += s;
+        if (sfactor > 1) {
+            if ((nonzero % (uint64_t)sfactor) == 0) { keep[r] = 1; kept += s; }
+        } else kept += s;
+    }
+    coarse[n_blocks] = total;
+    if (!base_path && total != n_entries_file) { set_error("bucket sizes sum to %llu entries but %llu were passed", (unsigned long long)total, (unsigned long long)n_entries_file); return CUCLARK_ERR_ARG; }
+
+    // largest chunk, for the staging buffers
+    uint64_t max_chunk_entries = 0;
+    for (uint64_t b0 = 0; b0 < n_blocks; b0 += CHUNK_BLOCKS) {
+        const uint64_t b1 = std::min<uint64_t>(b0 + CHUNK_BLOCKS, n_blocks);
+        max_chunk_entries = std::max(max_chunk_entries, coarse[b1] - coarse[b0]);
+    }
+    const uint64_t max_chunk_buckets = std::min<uint64_t>((uint64_t)CHUNK_BLOCKS * CHUNK_THREADS, H);
+
+    uint8_t *d_sz = nullptr, *d_keep = nullptr;
+    uint64_t* d_coarse = nullptr;
+    void* d_keys = nullptr;
+    uint16_t* d_labels = nullptr;
+    void* h_stage = nullptr;
+    auto free_stage = [&]() {
+        cudaFree(d_sz); cudaFree(d_keep); cudaFree(d_coarse); cudaFree(d_keys); cudaFree(d_labels);
+        if (h_stage) cudaFreeHost(h_stage);
+        d_sz = d_keep = nullptr; d_coarse = nullptr; d_keys = nullptr; d_labels = nullptr; h_stage = nullptr;
+    };
+    CK(cudaMalloc(&d_sz, max_chunk_buckets));
+    if (sfactor > 1) CK(cudaMalloc(&d_keep, max_chunk_buckets));
+    CK(cudaMalloc(&d_coarse, (CHUNK_BLOCKS + 1) * 8));
+    CK(cudaMalloc(&d_keys, std::max<uint64_t>(max_chunk_entries, 1) * kb));
+    CK(cudaMalloc(&d_labels, std::max<uint64_t>(max_chunk_entries, 1) * 2));
+    if (base_path) CK(cudaMallocHost(&h_stage, std::max<uint64_t>(max_chunk_entries, 1) * std::max(kb, 2)));
+
+    int rc = CUCLARK_ERR_BUILD;
+    double grow = 1.0;
+    for (int attempt = 0; attempt < 4 && rc == CUCLARK_ERR_BUILD; attempt++, grow *= 1.3) {
+        const Geometry g = choose_geometry(db->cfg, kept, grow);
+        BuildBuffers bb;
+        BuildCtx x{};
+        rc = alloc_build(g, kept / (db->cfg.shard_count > 1 ? db->cfg.shard_count : 1), bb, x, H);
+        if (rc != CUCLARK_OK) { bb.free_all(); break; }
+        if (base_path) { fseek(f_ky, 0, SEEK_SET); fseek(f_lb, 0, SEEK_SET); }
+        std::vector<uint64_t> rel(CHUNK_BLOCKS + 1);
+        for (uint64_t b0 = 0; b0 < n_blocks && rc == CUCLARK_OK; b0 += CHUNK_BLOCKS) {
+            const uint64_t b1 = std::min<uint64_t>(b0 + CHUNK_BLOCKS, n_blocks);
+            const uint64_t r0 = b0 * CHUNK_THREADS, r1 = std::min<uint64_t>(b1 * CHUNK_THREADS, H);
+            const uint64_t e0 = coarse[b0], ne = coarse[b1] - e0;
+            if (ne == 0) continue;
+            for (uint64_t b = b0; b <= b1; b++) rel[b - b0] = coarse[b] - e0;
+            auto cp = [&](void* dst, const void* src, size_t n) { return cudaMemcpy(dst, src, n, cudaMemcpyHostToDevice); };
+            cudaError_t e = cp(d_sz, sz + r0, r1 - r0);
+            if (e == cudaSuccess && sfactor > 1) e = cp(d_keep, keep.data() + r0, r1 - r0);
+            if (e == cudaSuccess) e = cp(d_coarse, rel.data(), (b1 - b0 + 1) * 8);
+            if (e == cudaSuccess) {
+                if (base_path) {
+                    if (fread(h_stage, kb, ne, f_ky) != ne) { set_error("%s.ky is short", base_path); rc = CUCLARK_ERR_IO; break; }
+                    e = cp(d_keys, h_stage, ne * kb);
+                    if (e == cudaSuccess) {
+                        if (fread(h_stage, 2, ne, f_lb) != ne) { set_error("%s.lb is short", base_path); rc = CUCLARK_ERR_IO; break; }
+                        e = cp(d_labels, h_stage, ne * 2);
+                    }
+                } else {
+                    e = cp(d_keys, static_cast<const uint8_t*>(ky) + e0 * kb, ne * kb);
+                    if (e == cudaSuccess) e = cp(d_labels, lb + e0, ne * 2);
+                }
+            }
+            if (e != cudaSuccess) { set_error("DB upload failed: %s", cudaGetErrorString(e)); rc = CUCLARK_ERR_CUDA; break; }
+            const unsigned blocks = (unsigned)(b1 - b0);
+            if (g.layout == LAYOUT_NARROW)
+                k_insert_chunk<LAYOUT_NARROW><<<blocks, CHUNK_THREADS>>>(x, d_sz, d_keep, d_coarse, r0, (uint32_t)(r1 - r0), d_keys, d_labels, kb);
+            else
+                k_insert_chunk<LAYOUT_WIDE><<<blocks, CHUNK_THREADS>>>(x, d_sz, d_keep, d_coarse, r0, (uint32_t)(r1 - r0), d_keys, d_labels, kb);
+            e = cudaGetLastError();
+            if (e == cudaSuccess) e = cudaDeviceSynchronize();   // staging buffers are reused
+            if (e != cudaSuccess) { set_error("insert kernel failed: %s", cudaGetErrorString(e)); rc = CUCLARK_ERR_CUDA; break; }
+        }
+        if (rc == CUCLARK_OK) rc = finish_build(db, g, bb, x, false);
+        if (rc != CUCLARK_OK) bb.free_all();
+    }
+    free_stage();
+    return rc;
+}
+
+int table_build_synthetic(cuclark_db* db, uint32_t seed, uint32_t n_targets, uint64_t genome_len, int light_gap) {
+    const int k = db->cfg.k;
+    if (genome_len < (uint64_t)k) { set_error("genome shorter than k"); return CUCLARK_ERR_ARG; }
+    uint64_t per_target, expected;
+    if (light_gap > 0) {
+        const uint64_t nk = genome_len / k;
+        per_target = (nk + light_gap - 1) / light_gap;
+    } else {
+        per_target = genome_len - k + 1;
+    }
+    expected = per_target * n_targets;
+    int rc = CUCLARK_ERR_BUILD;
+    double grow = 1.0;
+    for (int attempt = 0; attempt < 4 && rc == CUCLARK_ERR_BUILD; attempt++, grow *= 1.3) {
+        const Geometry g = choose_geometry(db->cfg, expected, grow);
+        BuildBuffers bb;
+        BuildCtx x{};
+        rc = alloc_build(g, expected / (db->cfg.shard_count > 1 ? db->cfg.shard_count : 1), bb, x, db->cfg.htsize);
+        if (rc != CUCLARK_OK) { bb.free_all(); break; }
+        if (light_gap > 0) {
+            const uint64_t n = per_target * n_targets;
+            const unsigned blocks = (unsigned)((n + 255) / 256);
+            if (g.layout == LAYOUT_NARROW) k_synth_insert_light<LAYOUT_NARROW><<<blocks, 256>>>(x, seed, n_targets, genome_len, k, light_gap, per_target);
+            else k_synth_insert_light<LAYOUT_WIDE><<<blocks, 256>>>(x, seed, n_targets, genome_len, k, light_gap, per_target);
+        } else {
+            const uint64_t runs = (per_target + 63) / 64;
+            const uint64_t n = runs * n_targets;
+            const unsigned blocks = (unsigned)((n + 127) / 128);
+            if (g.layout == LAYOUT_NARROW) k_synth_insert_full<LAYOUT_NARROW><<<blocks, 128>>>(x, seed, n_targets, genome_len, k, runs);
+            else k_synth_insert_full<LAYOUT_WIDE><<<blocks, 128>>>(x, seed, n_targets, genome_len, k, runs);
+        }
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { set_error("synthetic insert failed: %s", cudaGetErrorString(e)); bb.free_all(); return CUCLARK_ERR_CUDA; }
+        rc = finish_build(db, g, bb, x, true);
+        if (rc != CUCLARK_OK) bb.free_all();
+    }
+    return rc;
+}
+
+}  // namespace cuclark

@@ -1,0 +1,158 @@
+/*
+ * cuclark_b200.h — C ABI of libcuclark_b200.so
+ *
+ * B200-native replacement for the GPU driver class of CuCLARK,
+ * `CuClarkDB<HKMERr>` (reference: src/CuClarkDB.cuh:98-150, implementation
+ * src/CuClarkDB.cu:84-1033, kernels src/CuClarkDB.cu:1045-1471), i.e. the seam
+ * between the host orchestrator (src/CuCLARK_hh.hh) and the device:
+ * load the target-specific k-mer database, take batches of 2-bit packed reads,
+ * return per-read (sum, best, hits, second, hits) and, on request, the sparse
+ * per-target hit rows.
+ *
+ * Plain C types only. Every function returns CUCLARK_OK (0) or a negative
+ * error code; cuclark_last_error() gives the message of the calling thread's
+ * last failure. There is NO CPU fallback: without a CUDA device
+ * cuclark_create() fails with CUCLARK_ERR_NO_DEVICE.
+ *
+ * Data formats are the reference's own:
+ *   - database files  <base>.sz / .ky / .lb        src/hashTable_hh.hh:591-663
+ *   - packed reads    readsPointer[n+1] (uint32 container offsets) +
+ *                     containers (uint16: per part one length header, then
+ *                     8 nt per container, MSB first, code A=3 C=2 G=1 T=0)
+ *                                                  src/CuCLARK_hh.hh:1616-1708
+ *   - sparse row      uint16[2*row_pairs+2] = [n, (target, hits)*n] ascending
+ *                                                  src/CuClarkDB.cu:1181-1243
+ *   - final result    uint16[5] = [sum, best+1, hits, second+1, hits]
+ *                                                  src/CuClarkDB.cu:1421-1471
+ */
+#ifndef CUCLARK_B200_H
+#define CUCLARK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CUCLARK_OK 0
+#define CUCLARK_ERR_ARG (-1)
+#define CUCLARK_ERR_NO_DEVICE (-2)
+#define CUCLARK_ERR_CUDA (-3)
+#define CUCLARK_ERR_IO (-4)        /* a database file is missing/short: CuClarkDB::read returns false */
+#define CUCLARK_ERR_NOMEM (-5)
+#define CUCLARK_ERR_STATE (-6)     /* call order violated (no DB loaded, batch not ready, ...) */
+#define CUCLARK_ERR_BUILD (-7)     /* device table could not be built (bucket overflow) */
+
+/* reference constants (src/parameters.hh:38-48, src/parameters_light_hh:39-49) */
+#define CUCLARK_HTSIZE_FULL 1610612741ull
+#define CUCLARK_HTSIZE_LIGHT 57777779ull
+#define CUCLARK_MAXHITS_FULL 15
+#define CUCLARK_MAXHITS_LIGHT 23
+
+typedef struct cuclark_db cuclark_db;
+
+/* Replaces the CuClarkDB constructor arguments (src/CuClarkDB.cu:85-108) and
+ * the compile-time variant (HTSIZE/MAXHITS by header swap, src/Makefile:26-34),
+ * which is a run-time choice here. */
+typedef struct cuclark_config {
+    int k;                /* k-mer length, 2..32 (src/main.cc:107-112)                       */
+    uint64_t htsize;      /* HTSIZE of the database FILES (full or light)                    */
+    int key_bytes;        /* width of a .ky element: 2, 4, 8; 0 = as src/main.cc:278-316     */
+    int n_targets;        /* number of labels (CuClarkDB ctor _numTargets)                   */
+    int row_pairs;        /* MAXHITS: (target,hits) pairs per sparse row; 0 = by htsize      */
+    int device;           /* CUDA device ordinal                                             */
+    int shard_index;      /* table-partitioned mode: this handle holds shard i of n          */
+    int shard_count;      /*   (contiguous ranges of device buckets); 1 = whole table        */
+    double bucket_load;   /* mean entries per 32-byte bucket; 0 = default                    */
+    int layout;           /* 0 auto, 1 narrow (5 x 32-bit key), 2 wide (3 x 64-bit key)      */
+} cuclark_config;
+
+typedef struct cuclark_stats {
+    uint64_t n_entries;        /* entries held by this shard                                 */
+    uint64_t n_buckets;        /* global bucket count M                                      */
+    uint64_t n_local_buckets;  /* buckets held by this shard                                 */
+    uint64_t table_bytes;      /* device bytes of this shard's table                         */
+    uint64_t n_spilled;        /* entries stored outside their home bucket                   */
+    uint64_t n_spill_buckets;  /* buckets with maxdisp > 0                                   */
+    int layout;                /* 1 narrow, 2 wide                                           */
+    int k;
+    uint64_t lookups;          /* k-mers looked up by the last classify call                 */
+    uint64_t dense_reads;      /* reads of the last call that took the dense fallback        */
+    uint64_t truncated_rows;   /* rows of the last call with more than row_pairs targets     */
+    double last_kernel_ms;     /* device time of the last classify (CUDA events)             */
+} cuclark_stats;
+
+const char* cuclark_last_error(void);
+int cuclark_version(void);
+
+/* CuClarkDB::CuClarkDB / ~CuClarkDB (src/CuClarkDB.cu:85-208, 215-260) */
+int cuclark_create(const cuclark_config* cfg, cuclark_db** out);
+int cuclark_destroy(cuclark_db* db);
+
+/* CuClarkDB::read + swapDbParts + sync (src/CuClarkDB.cu:462-858): loads
+ * <base>.sz/.ky/.lb, applies -s sampling (:511-524), re-buckets on the device.
+ * CUCLARK_ERR_IO if a file cannot be opened (the reference returns false). */
+int cuclark_load_db_files(cuclark_db* db, const char* base, int sfactor);
+/* same from host arrays (sz: htsize bytes; ky: n_entries keys of key_bytes; lb) */
+int cuclark_load_db_arrays(cuclark_db* db, const uint8_t* sz, const void* ky, const uint16_t* lb,
+                           uint64_t n_entries, int sfactor);
+/* Synthetic database built ON the device (bench.py at BASELINE sizes): all
+ * canonical k-mers of n_targets seeded random genomes of genome_len bases
+ * (stride 1 = every overlapping k-mer, as the full variant; the light variant
+ * samples every `stride`-th non-overlapping k-mer), label = target, k-mers seen
+ * in more than one target removed (RemoveCommon, src/HashTableStorage_hh.hh:242-292). */
+int cuclark_build_db_synthetic(cuclark_db* db, uint32_t seed, uint32_t n_targets, uint64_t genome_len,
+                               int light_gap);
+
+int cuclark_get_stats(cuclark_db* db, cuclark_stats* out);
+/* Fetch the counters (lookups, dense_reads, truncated_rows) of the last
+ * cuclark_classify_device call; synchronises `stream` (NULL = library stream). */
+int cuclark_sync_stats(cuclark_db* db, void* stream);
+
+/* ---- batches: CuClarkDB::malloc / readyBatch / queryBatch / waitForBatch /
+ * freeBatchMemory (src/CuClarkDB.cu:318-460, 861-1033). The library owns
+ * pinned host buffers, the caller fills them (pack loop) and reads results. */
+int cuclark_batches_alloc(cuclark_db* db, int n_batches, size_t max_reads, size_t max_containers,
+                          int want_rows);
+int cuclark_batch_buffers(cuclark_db* db, int batch, uint32_t** reads_ptr, uint16_t** containers,
+                          uint16_t** final5, uint16_t** rows);
+int cuclark_batch_ready(cuclark_db* db, int batch, size_t n_reads, size_t n_containers);
+int cuclark_batch_query(cuclark_db* db, int batch);   /* async: H2D, kernels, D2H, event */
+int cuclark_batch_wait(cuclark_db* db, int batch);
+int cuclark_batches_free(cuclark_db* db);
+
+/* One-shot convenience over host buffers (pageable or pinned). rows may be NULL. */
+int cuclark_classify_host(cuclark_db* db, const uint32_t* reads_ptr, const uint16_t* containers,
+                          size_t n_reads, uint16_t* final5, uint16_t* rows);
+
+/* Device-resident inputs and outputs (all pointers are device pointers on
+ * cfg.device; stream is a cudaStream_t or NULL). d_final5 and d_rows may each
+ * be NULL. With shard_count > 1 only rows are meaningful (merge them first). */
+int cuclark_classify_device(cuclark_db* db, const uint32_t* d_reads_ptr, const uint16_t* d_containers,
+                            size_t n_reads, uint16_t* d_final5, uint16_t* d_rows, void* stream);
+
+/* mergeKernel + resultKernel (src/CuClarkDB.cu:1321-1471) generalised to n_parts
+ * shards: d_rows_parts holds n_parts consecutive row arrays [part][read][pitch].
+ * Writes merged rows (may be NULL) and final results (may be NULL). */
+int cuclark_merge_rows_device(cuclark_db* db, const uint16_t* d_rows_parts, int n_parts, size_t n_reads,
+                              uint16_t* d_rows_out, uint16_t* d_final5, void* stream);
+
+/* ---- synthetic reads generated on the device (bench.py): packed format ---- */
+/* Fills d_reads_ptr[n_reads+1] and d_containers (n_reads * (1+ceil(read_len/8)))
+ * with reads sampled from the synthetic genomes of cuclark_build_db_synthetic. */
+int cuclark_synth_reads_device(cuclark_db* db, uint32_t seed, uint32_t genome_seed, uint32_t n_targets,
+                               uint64_t genome_len, uint64_t first_read, size_t n_reads, int read_len,
+                               int pct_random, int sub_per_10k, uint32_t* d_reads_ptr,
+                               uint16_t* d_containers, void* stream);
+
+/* ---- roofline probe: random 32-byte-sector gather over this table ---------- */
+/* Reads n_probes uniformly random sectors of the loaded table per launch
+ * (ilp independent loads per thread); returns average ms over `iters` launches. */
+int cuclark_gather_bench(cuclark_db* db, uint64_t n_probes, int bytes_per_probe, int ilp, int iters,
+                         double* ms_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CUCLARK_B200_H */

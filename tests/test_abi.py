@@ -1,0 +1,67 @@
+"""CPU: the C-ABI library builds, loads and exports every symbol include/cuclark_b200.h declares."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from cuclark_b200 import api
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "cuclark_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(cuclark_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from cuclark_b200 import build
+    build.build_lib()
+    lib = ctypes.CDLL(api.LIB_PATH)
+    names = declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/cuclark_b200.h but not exported"
+    assert set(names) == set(api.ABI_SYMBOLS)
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product refuses to run (it never routes to the oracle)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(api.CuclarkError) as e:
+        api.CuClarkDB(31, 10)
+    assert e.value.code == -2 and "no CPU fallback" in str(e.value)
+
+
+def test_argument_validation():
+    lib = api.load_library()
+    h = ctypes.c_void_p()
+    cfg = api.Config(33, api.HTSIZE_FULL, 0, 10, 0, 0, 0, 1, 0.0, 0)
+    assert lib.cuclark_create(ctypes.byref(cfg), ctypes.byref(h)) == -1
+    assert b"[2,32]" in lib.cuclark_last_error()
+    cfg = api.Config(31, api.HTSIZE_FULL, 0, 0, 0, 0, 0, 1, 0.0, 0)
+    assert lib.cuclark_create(ctypes.byref(cfg), ctypes.byref(h)) == -1
+
+
+def test_product_does_not_import_oracle():
+    """Nothing under cuclark_b200/ may import, link or execute oracle/."""
+    pkg = os.path.join(ROOT, "cuclark_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cc", ".cpp", ".hh")):
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "liboracle" not in text and "from oracle" not in text and "import oracle" not in text, f
+                assert "cuclark_oracle" not in text, f
+
+
+def test_key_width_dispatch():
+    # src/main.cc:278-316
+    assert api.key_bytes_for(31, api.HTSIZE_FULL) == 4
+    assert api.key_bytes_for(23, api.HTSIZE_FULL) == 2
+    assert api.key_bytes_for(32, api.HTSIZE_FULL) == 8
+    assert api.key_bytes_for(27, api.HTSIZE_LIGHT) == 4
+    assert api.key_bytes_for(20, api.HTSIZE_LIGHT) == 2
