@@ -180,7 +180,7 @@ int cuclark_get_stats(cuclark_db* db, cuclark_stats* s) {
     s->n_entries = db->n_entries;
     s->n_buckets = db->view.M;
     s->n_local_buckets = db->view.n_local;
-    s->table_bytes = db->view.n_local * 32;
+    s->table_bytes = (db->view.n_local + db->view.n_ovf) * 32;
     s->n_spilled = db->n_spilled;
     s->n_spill_buckets = db->n_spill_buckets;
     s->layout = db->view.layout;

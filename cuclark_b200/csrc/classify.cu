@@ -129,14 +129,9 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_classify(const Classif
                     for (int j = 0; j < ILP_ROUNDS; j++) {
                         uint32_t label = NO_LABEL;
                         if (live[j]) {
-                            label = match_sector<LAYOUT>(sec[j], q[j], 0);
-                            const uint32_t md = sector_maxdisp(sec[j]);
-                            for (uint32_t d = 1; label == NO_LABEL && d <= md; d++) {
-                                uint64_t nb = lb[j] + d;
-                                if (nb >= T.n_local) nb -= T.n_local;
-                                const Sector s2 = load_sector(T.buckets + 2 * nb);
-                                label = match_sector<LAYOUT>(s2, q[j], d);
-                            }
+                            label = match_sector<LAYOUT>(sec[j], q[j]);
+                            if (label == NO_LABEL && sector_overflowed(sec[j]))
+                                label = ovf_lookup(T, q[j] * T.M + (lb[j] + T.lo));
                             if (label >= p.n_targets) label = NO_LABEL;
                         }
                         const uint32_t hitmask = __ballot_sync(0xFFFFFFFFu, label != NO_LABEL);

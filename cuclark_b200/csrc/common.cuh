@@ -13,18 +13,20 @@
 //     word 5      label[0] | label[1] << 16
 //     word 6      label[2] | label[3] << 16
 //     word 7      label[4] | meta << 16
-//   WIDE (any k <= 32, any M; used for small tables):
+//   WIDE (any k <= 32, any M; used for small tables and the overflow table):
 //     word 0..5   key[0..2] as uint64  (all-ones = empty)
 //     word 6      label[0] | label[1] << 16
 //     word 7      label[2] | meta << 16
 //
-//   meta (16 bit): bits 0..1  maxdisp  = how far entries homed HERE spilled (0..3)
-//                  bits 2+2i..3+2i     disp[i] = distance of slot i from ITS home
-//   A bucket that is full spills into the next 1..3 buckets (same shard). A
-//   lookup reads its home sector, and only if maxdisp > 0 and the key was not
-//   found does it read home+1..home+maxdisp. With a mean load of ~2.5 entries
-//   per 5-slot bucket ~4% of buckets spill, so the expected cost is ~1.04
-//   sectors per lookup for hits and misses alike.
+//   meta bit 0 = "overflowed": more k-mers are homed here than the bucket has
+//   slots; the excess lives in the OVERFLOW table, a second, sparsely filled
+//   array of WIDE buckets keyed by the full canonical k-mer, addressed by an
+//   independent hash and resolved by linear probing over buckets (a bucket with
+//   a free slot ends the probe sequence; removed entries leave a tombstone).
+//   A lookup reads its home sector and, only when the key is not there AND the
+//   bucket is flagged, continues in the overflow table. At ~2.5 entries per
+//   5-slot bucket ~4% of the buckets are flagged: ~1.04 sectors per lookup for
+//   hits and misses alike.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -36,15 +38,19 @@ constexpr int LAYOUT_NARROW = 1;
 constexpr int LAYOUT_WIDE = 2;
 constexpr int NARROW_SLOTS = 5;
 constexpr int WIDE_SLOTS = 3;
-constexpr int MAX_DISP = 3;
 constexpr uint32_t NO_LABEL = 0xFFFFFFFFu;
+constexpr uint64_t OVF_EMPTY = ~0ull;
+constexpr uint64_t OVF_TOMBSTONE = ~0ull - 1;
+constexpr uint64_t OVF_HASH_MULT = 0x9E3779B97F4A7C15ull;
 
 struct TableView {
     const uint4* buckets;   // 2 x uint4 per bucket, 32-byte aligned
+    const uint4* ovf;       // overflow table (WIDE buckets, full k-mers), may be null
     uint64_t M;             // global number of buckets (the modulus)
     uint64_t magic;         // floor(2^64 / M)
     uint64_t lo;            // this shard holds home buckets [lo, lo+n_local)
     uint64_t n_local;
+    uint64_t n_ovf;         // buckets in the overflow table
     int layout;
     int k;
 };
@@ -94,36 +100,53 @@ __device__ __forceinline__ Sector load_sector(const uint4* p) {
     return s;
 }
 
-// Match `key` among the slots of a sector whose displacement equals d.
-// Returns the label or NO_LABEL. Empty slots hold an all-ones key, which no
-// valid quotient equals (M is chosen so that quotients stay below it).
+// Match `key` among the slots of a sector. Returns the label or NO_LABEL.
+// Empty slots hold an all-ones key, which no valid quotient equals (M is chosen
+// so that quotients stay below it).
 template <int LAYOUT>
-__device__ __forceinline__ uint32_t match_sector(const Sector& s, uint64_t key, uint32_t d) {
-    const uint32_t meta = s.w[7] >> 16;
+__device__ __forceinline__ uint32_t match_sector(const Sector& s, uint64_t key) {
     uint32_t label = NO_LABEL;
     if (LAYOUT == LAYOUT_NARROW) {
         const uint32_t k32 = (uint32_t)key;
 #pragma unroll
         for (int i = 0; i < NARROW_SLOTS; i++) {
-            const uint32_t disp = (meta >> (2 + 2 * i)) & 3u;
             const uint32_t lw = s.w[5 + (i >> 1)];
-            const uint32_t l = (i & 1) ? (lw >> 16) : (lw & 0xFFFFu);
-            if (s.w[i] == k32 && disp == d) label = l;
+            if (s.w[i] == k32) label = (i & 1) ? (lw >> 16) : (lw & 0xFFFFu);
         }
     } else {
 #pragma unroll
         for (int i = 0; i < WIDE_SLOTS; i++) {
             const uint64_t kk = (uint64_t)s.w[2 * i] | ((uint64_t)s.w[2 * i + 1] << 32);
-            const uint32_t disp = (meta >> (2 + 2 * i)) & 3u;
             const uint32_t lw = s.w[6 + (i >> 1)];
-            const uint32_t l = (i & 1) ? (lw >> 16) : (lw & 0xFFFFu);
-            if (kk == key && disp == d) label = l;
+            if (kk == key) label = (i & 1) ? (lw >> 16) : (lw & 0xFFFFu);
         }
     }
     return label;
 }
 
-__device__ __forceinline__ uint32_t sector_maxdisp(const Sector& s) { return (s.w[7] >> 16) & 3u; }
+__device__ __forceinline__ bool sector_overflowed(const Sector& s) { return (s.w[7] >> 16) & 1u; }
+
+__host__ __device__ __forceinline__ uint64_t ovf_home(uint64_t c, uint64_t n_ovf) {
+#ifdef __CUDA_ARCH__
+    return __umul64hi(c * OVF_HASH_MULT, n_ovf);
+#else
+    return (uint64_t)(((__uint128_t)(c * OVF_HASH_MULT) * n_ovf) >> 64);
+#endif
+}
+
+// Overflow table: linear probing over WIDE buckets holding the full k-mer.
+__device__ __forceinline__ uint32_t ovf_lookup(const TableView& t, uint64_t c) {
+    uint64_t b = ovf_home(c, t.n_ovf);
+    for (uint64_t n = 0; n < t.n_ovf; n++) {
+        const Sector s = load_sector(t.ovf + 2 * b);
+        const uint32_t label = match_sector<LAYOUT_WIDE>(s, c);
+        if (label != NO_LABEL) return label;
+        // a free slot ends the sequence (slots fill in order, so test the last one)
+        if (((uint64_t)s.w[4] | ((uint64_t)s.w[5] << 32)) == OVF_EMPTY) return NO_LABEL;
+        if (++b == t.n_ovf) b = 0;
+    }
+    return NO_LABEL;
+}
 
 // Full lookup of one canonical k-mer (used by the slow paths; the hot kernel
 // inlines the same steps so that it can batch the home-sector loads).
@@ -131,17 +154,11 @@ template <int LAYOUT>
 __device__ __forceinline__ uint32_t table_lookup(const TableView& t, uint64_t c) {
     uint64_t q, b;
     divmod_M(c, t.M, t.magic, q, b);
-    uint64_t lb = b - t.lo;
+    const uint64_t lb = b - t.lo;
     if (lb >= t.n_local) return NO_LABEL;           // other shard (b < lo wraps around)
-    Sector s = load_sector(t.buckets + 2 * lb);
-    uint32_t label = match_sector<LAYOUT>(s, q, 0);
-    uint32_t md = sector_maxdisp(s);
-    for (uint32_t d = 1; label == NO_LABEL && d <= md; d++) {
-        uint64_t nb = lb + d;
-        if (nb >= t.n_local) nb -= t.n_local;
-        Sector s2 = load_sector(t.buckets + 2 * nb);
-        label = match_sector<LAYOUT>(s2, q, d);
-    }
+    const Sector s = load_sector(t.buckets + 2 * lb);
+    uint32_t label = match_sector<LAYOUT>(s, q);
+    if (label == NO_LABEL && sector_overflowed(s)) label = ovf_lookup(t, c);
     return label;
 }
 

@@ -47,6 +47,7 @@ struct cuclark_db {
     int key_bytes;
     // device table
     uint4* d_table = nullptr;
+    uint4* d_ovf = nullptr;            // overflow table
     cuclark::TableView view{};
     uint64_t n_entries = 0, n_spilled = 0, n_spill_buckets = 0;
     // classify scratch (one-shot calls; batches carry their own)

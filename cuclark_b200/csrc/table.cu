@@ -23,6 +23,7 @@ namespace cuclark {
 namespace {
 
 constexpr uint32_t ERR_OVF_LIST = 1, ERR_COUNTER = 2, ERR_NO_SLOT = 4;
+constexpr double OVF_LOAD = 0.75;                  // mean entries per 3-slot overflow bucket
 constexpr int CHUNK_THREADS = 1024;
 constexpr uint32_t CHUNK_BLOCKS = 16384;           // 16.7M reference buckets per chunk
 
@@ -35,11 +36,13 @@ struct BuildCtx {
     uint32_t ovf_cap;
     uint32_t* flags;       // [0] overflow count, [1] error bits
     unsigned long long* inserted;   // entries homed in this shard
+    uint4* ovf;            // overflow table (allocated after phase 1)
+    uint32_t* ovf_cnt8;
+    uint64_t n_ovf;
 };
 
 template <int LAYOUT>
-__device__ __forceinline__ void write_slot(uint4* table, uint64_t lb, uint32_t slot, uint64_t q, uint32_t label,
-                                           uint32_t d) {
+__device__ __forceinline__ void write_slot(uint4* table, uint64_t lb, uint32_t slot, uint64_t q, uint32_t label) {
     uint32_t* w = reinterpret_cast<uint32_t*>(table + 2 * lb);
     if (LAYOUT == LAYOUT_NARROW) {
         w[slot] = (uint32_t)q;
@@ -48,13 +51,12 @@ __device__ __forceinline__ void write_slot(uint4* table, uint64_t lb, uint32_t s
         reinterpret_cast<uint64_t*>(w)[slot] = q;
         atomicOr(&w[6 + (slot >> 1)], label << (16 * (slot & 1)));
     }
-    if (d) atomicOr(&w[7], d << (16 + 2 + 2 * slot));
 }
 
-__device__ __forceinline__ uint32_t claim_slot(const BuildCtx& x, uint64_t lb) {
+__device__ __forceinline__ uint32_t claim_slot(uint32_t* cnt8, uint32_t* flags, uint64_t lb) {
     const uint32_t sh = 8 * (uint32_t)(lb & 3);
-    const uint32_t old = (atomicAdd(&x.cnt8[lb >> 2], 1u << sh) >> sh) & 0xFFu;
-    if (old == 255u) atomicOr(&x.flags[1], ERR_COUNTER);
+    const uint32_t old = (atomicAdd(&cnt8[lb >> 2], 1u << sh) >> sh) & 0xFFu;
+    if (old == 255u) atomicOr(&flags[1], ERR_COUNTER);
     return old;
 }
 
@@ -65,9 +67,9 @@ __device__ __forceinline__ bool insert_home(const BuildCtx& x, uint64_t c, uint3
     divmod_M(c, x.M, x.magic, q, b);
     const uint64_t lb = b - x.lo;
     if (lb >= x.n_local) return false;               // homed in another shard
-    const uint32_t slot = claim_slot(x, lb);
+    const uint32_t slot = claim_slot(x.cnt8, x.flags, lb);
     if (slot < SLOTS) {
-        write_slot<LAYOUT>(x.table, lb, slot, q, label, 0);
+        write_slot<LAYOUT>(x.table, lb, slot, q, label);
     } else {
         const uint32_t i = atomicAdd(&x.flags[0], 1u);
         if (i < x.ovf_cap) { x.ovf_c[i] = c; x.ovf_l[i] = (uint16_t)label; }
@@ -132,10 +134,9 @@ __global__ void __launch_bounds__(CHUNK_THREADS) k_insert_chunk(BuildCtx x, cons
     if (mine) atomicAdd(x.inserted, mine);
 }
 
-// Entries whose home bucket was full go to the next 1..MAX_DISP buckets.
-template <int LAYOUT>
+// Entries whose home bucket was full: flag the home bucket and put the full
+// k-mer into the overflow table (linear probing over WIDE buckets).
 __global__ void k_place_spills(BuildCtx x, uint32_t n) {
-    constexpr uint32_t SLOTS = LAYOUT == LAYOUT_NARROW ? NARROW_SLOTS : WIDE_SLOTS;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint64_t c = x.ovf_c[i];
@@ -143,21 +144,16 @@ __global__ void k_place_spills(BuildCtx x, uint32_t n) {
     uint64_t q, b;
     divmod_M(c, x.M, x.magic, q, b);
     const uint64_t lb = b - x.lo;
-    for (uint32_t d = 1; d <= (uint32_t)MAX_DISP; d++) {
-        uint64_t nb = lb + d;
-        if (nb >= x.n_local) nb -= x.n_local;
-        const uint32_t slot = claim_slot(x, nb);
-        if (slot >= SLOTS) continue;
-        write_slot<LAYOUT>(x.table, nb, slot, q, label, d);
-        // raise maxdisp (meta bits 0..1) of the HOME bucket to at least d
-        uint32_t* w7 = reinterpret_cast<uint32_t*>(x.table + 2 * lb) + 7;
-        uint32_t old = *w7;
-        while (((old >> 16) & 3u) < d) {
-            const uint32_t assumed = old;
-            old = atomicCAS(w7, assumed, (assumed & ~(3u << 16)) | (d << 16));
-            if (old == assumed) break;
+    atomicOr(reinterpret_cast<uint32_t*>(x.table + 2 * lb) + 7, 1u << 16);
+    uint64_t ob = ovf_home(c, x.n_ovf);
+    for (uint64_t n_try = 0; n_try < x.n_ovf; n_try++) {
+        // the counter saturates logically at WIDE_SLOTS; do not wrap its byte
+        const uint32_t sh = 8 * (uint32_t)(ob & 3);
+        if (((__ldcg(&x.ovf_cnt8[ob >> 2]) >> sh) & 0xFFu) < (uint32_t)WIDE_SLOTS) {
+            const uint32_t slot = claim_slot(x.ovf_cnt8, x.flags, ob);
+            if (slot < (uint32_t)WIDE_SLOTS) { write_slot<LAYOUT_WIDE>(x.ovf, ob, slot, c, label); return; }
         }
-        return;
+        if (++ob == x.n_ovf) ob = 0;
     }
     atomicOr(&x.flags[1], ERR_NO_SLOT);
 }
@@ -165,7 +161,7 @@ __global__ void k_place_spills(BuildCtx x, uint32_t n) {
 __global__ void k_table_stats(const uint4* table, uint64_t n_local, unsigned long long* out) {
     const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     bool spill = false;
-    if (i < n_local) spill = ((table[2 * i + 1].w >> 16) & 3u) != 0;
+    if (i < n_local) spill = ((table[2 * i + 1].w >> 16) & 1u) != 0;
     const uint32_t m = __ballot_sync(0xFFFFFFFFu, spill);
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(out, (unsigned long long)__popc(m));
 }
@@ -208,65 +204,142 @@ __global__ void k_synth_insert_light(BuildCtx x, uint32_t seed, uint32_t n_targe
 
 // RemoveCommon (src/HashTableStorage_hh.hh:242-292) for the synthetic builder:
 // a k-mer inserted more than once is kept once if all copies carry the same
-// label and removed entirely otherwise. All copies share one home bucket.
+// label and removed entirely otherwise. Copies of one k-mer sit in its home
+// bucket and/or along its overflow probe sequence. Two read-only passes compute
+// a verdict per slot (no races), a third applies them.
 template <int LAYOUT>
-__global__ void k_dedupe(uint4* table, uint64_t n_local, unsigned long long* removed) {
+struct DedupeView {
+    uint4* table; uint4* ovf; uint64_t M, lo, n_local, n_ovf;
+    uint8_t* del_main; uint8_t* del_ovf;
+};
+
+__device__ __forceinline__ uint64_t wide_key(const uint32_t* w, int s) { return reinterpret_cast<const uint64_t*>(w)[s]; }
+__device__ __forceinline__ uint32_t wide_label(const uint32_t* w, int s) { const uint32_t lw = w[6 + (s >> 1)]; return (s & 1) ? (lw >> 16) : (lw & 0xFFFFu); }
+
+// scan the overflow probe sequence of c: sets differ if a copy with another label
+// exists; returns the number of copies seen strictly before (stop_b, stop_s)
+// (pass stop_b = ~0 to count all copies).
+__device__ __forceinline__ uint32_t ovf_scan(const uint4* ovf, uint64_t n_ovf, uint64_t c, uint32_t label,
+                                             uint64_t stop_b, int stop_s, bool& differ, uint32_t& total) {
+    uint32_t before = 0;
+    bool passed = false;
+    total = 0;
+    uint64_t b = ovf_home(c, n_ovf);
+    for (uint64_t n = 0; n < n_ovf; n++) {
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(ovf + 2 * b);
+        for (int s = 0; s < WIDE_SLOTS; s++) {
+            if (b == stop_b && s == stop_s) { passed = true; continue; }
+            if (wide_key(w, s) != c) continue;
+            total++;
+            if (!passed) before++;
+            if (wide_label(w, s) != label) differ = true;
+        }
+        if (wide_key(w, WIDE_SLOTS - 1) == OVF_EMPTY) break;
+        if (++b == n_ovf) b = 0;
+    }
+    return before;
+}
+
+template <int LAYOUT>
+__global__ void k_dedupe_main(DedupeView<LAYOUT> v) {
     constexpr int SLOTS = LAYOUT == LAYOUT_NARROW ? NARROW_SLOTS : WIDE_SLOTS;
-    constexpr int CAP = SLOTS * (MAX_DISP + 1);
     const uint64_t lb = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (lb >= n_local) return;
-    uint32_t* home = reinterpret_cast<uint32_t*>(table + 2 * lb);
-    const uint32_t md = (home[7] >> 16) & 3u;
-    uint64_t keys[CAP];
-    uint32_t labels[CAP];
-    uint32_t where[CAP];   // d * 8 + slot
-    int n = 0;
-    for (uint32_t d = 0; d <= md; d++) {
-        uint64_t nb = lb + d;
-        if (nb >= n_local) nb -= n_local;
-        const uint32_t* w = reinterpret_cast<const uint32_t*>(table + 2 * nb);
-        const uint32_t meta = w[7] >> 16;
-        for (int s = 0; s < SLOTS; s++) {
-            if (((meta >> (2 + 2 * s)) & 3u) != d) continue;
-            uint64_t kk;
-            uint32_t lw;
-            if (LAYOUT == LAYOUT_NARROW) {
-                if (w[s] == 0xFFFFFFFFu) continue;
-                kk = w[s];
-                lw = w[5 + (s >> 1)];
-            } else {
-                kk = reinterpret_cast<const uint64_t*>(w)[s];
-                if (kk == ~0ull) continue;
-                lw = w[6 + (s >> 1)];
-            }
-            keys[n] = kk;
-            labels[n] = (s & 1) ? (lw >> 16) : (lw & 0xFFFFu);
-            where[n] = d * 8 + s;
-            n++;
+    if (lb >= v.n_local) return;
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(v.table + 2 * lb);
+    const bool flagged = (w[7] >> 16) & 1u;
+    uint64_t keys[SLOTS];
+    uint32_t labels[SLOTS];
+    bool used[SLOTS];
+    for (int s = 0; s < SLOTS; s++) {
+        if (LAYOUT == LAYOUT_NARROW) {
+            keys[s] = w[s]; used[s] = w[s] != 0xFFFFFFFFu;
+            const uint32_t lw = w[5 + (s >> 1)];
+            labels[s] = (s & 1) ? (lw >> 16) : (lw & 0xFFFFu);
+        } else {
+            keys[s] = wide_key(w, s); used[s] = keys[s] != OVF_EMPTY;
+            labels[s] = wide_label(w, s);
         }
     }
-    unsigned long long gone = 0;
-    for (int i = 0; i < n; i++) {
-        if (where[i] == 0xFFFFFFFFu) continue;
-        bool common = false, dup = false;
-        for (int j = i + 1; j < n; j++) {
-            if (where[j] == 0xFFFFFFFFu || keys[j] != keys[i]) continue;
-            dup = true;
-            if (labels[j] != labels[i]) common = true;
+    uint32_t del = 0;
+    for (int i = 0; i < SLOTS; i++) {
+        if (!used[i]) continue;
+        bool differ = false, earlier = false;
+        for (int j = 0; j < SLOTS; j++) {
+            if (j == i || !used[j] || keys[j] != keys[i]) continue;
+            if (labels[j] != labels[i]) differ = true;
+            if (j < i) earlier = true;
         }
-        if (!dup) continue;
-        for (int j = i + (common ? 0 : 1); j < n; j++) {
-            if (where[j] == 0xFFFFFFFFu || keys[j] != keys[i]) continue;
-            const uint32_t d = where[j] >> 3, s = where[j] & 7;
-            uint64_t nb = lb + d;
-            if (nb >= n_local) nb -= n_local;
-            uint32_t* w = reinterpret_cast<uint32_t*>(table + 2 * nb);
+        if (flagged && v.n_ovf) {
+            uint32_t total;
+            ovf_scan(v.ovf, v.n_ovf, keys[i] * v.M + (lb + v.lo), labels[i], ~0ull, 0, differ, total);
+        }
+        if (differ || earlier) del |= 1u << i;      // main copies precede overflow copies
+    }
+    v.del_main[lb] = (uint8_t)del;
+}
+
+template <int LAYOUT>
+__global__ void k_dedupe_ovf(DedupeView<LAYOUT> v, uint64_t magic) {
+    constexpr int SLOTS = LAYOUT == LAYOUT_NARROW ? NARROW_SLOTS : WIDE_SLOTS;
+    const uint64_t ob = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (ob >= v.n_ovf) return;
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(v.ovf + 2 * ob);
+    uint32_t del = 0;
+    for (int s = 0; s < WIDE_SLOTS; s++) {
+        const uint64_t c = wide_key(w, s);
+        if (c == OVF_EMPTY) break;
+        const uint32_t label = wide_label(w, s);
+        bool differ = false;
+        uint32_t total;
+        const uint32_t before = ovf_scan(v.ovf, v.n_ovf, c, label, ob, s, differ, total);
+        // copies in the home bucket
+        uint64_t q, b;
+        divmod_M(c, v.M, magic, q, b);
+        const uint32_t* hw = reinterpret_cast<const uint32_t*>(v.table + 2 * (b - v.lo));
+        bool in_main = false;
+        for (int j = 0; j < SLOTS; j++) {
+            uint64_t kk; uint32_t ll;
+            if (LAYOUT == LAYOUT_NARROW) {
+                if (hw[j] == 0xFFFFFFFFu) continue;
+                kk = hw[j];
+                const uint32_t lw = hw[5 + (j >> 1)];
+                ll = (j & 1) ? (lw >> 16) : (lw & 0xFFFFu);
+            } else {
+                kk = wide_key(hw, j);
+                if (kk == OVF_EMPTY) continue;
+                ll = wide_label(hw, j);
+            }
+            if (kk != q) continue;
+            in_main = true;
+            if (ll != label) differ = true;
+        }
+        if (differ || in_main || before) del |= 1u << s;
+    }
+    v.del_ovf[ob] = (uint8_t)del;
+}
+
+template <int LAYOUT>
+__global__ void k_dedupe_apply(DedupeView<LAYOUT> v, unsigned long long* removed) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    unsigned long long gone = 0;
+    if (i < v.n_local && v.del_main[i]) {
+        uint32_t* w = reinterpret_cast<uint32_t*>(v.table + 2 * i);
+        const uint32_t del = v.del_main[i];
+        for (int s = 0; s < (LAYOUT == LAYOUT_NARROW ? NARROW_SLOTS : WIDE_SLOTS); s++) {
+            if (!((del >> s) & 1u)) continue;
             if (LAYOUT == LAYOUT_NARROW) w[s] = 0xFFFFFFFFu;
-            else reinterpret_cast<uint64_t*>(w)[s] = ~0ull;
-            if (j != i) where[j] = 0xFFFFFFFFu;
+            else reinterpret_cast<uint64_t*>(w)[s] = OVF_EMPTY;
             gone++;
         }
-        where[i] = 0xFFFFFFFFu;
+    }
+    if (i < v.n_ovf && v.del_ovf[i]) {
+        uint32_t* w = reinterpret_cast<uint32_t*>(v.ovf + 2 * i);
+        const uint32_t del = v.del_ovf[i];
+        for (int s = 0; s < WIDE_SLOTS; s++) {
+            if (!((del >> s) & 1u)) continue;
+            reinterpret_cast<uint64_t*>(w)[s] = OVF_TOMBSTONE;     // keeps the probe sequence intact
+            gone++;
+        }
     }
     if (gone) atomicAdd(removed, gone);
 }
@@ -311,6 +384,10 @@ Geometry choose_geometry(const cuclark_config& cfg, uint64_t n_entries, double g
 
 struct BuildBuffers {
     uint4* table = nullptr;
+    uint4* ovf = nullptr;
+    uint32_t* ovf_cnt8 = nullptr;
+    uint8_t* del_main = nullptr;
+    uint8_t* del_ovf = nullptr;
     uint32_t* cnt8 = nullptr;
     uint64_t* ovf_c = nullptr;
     uint16_t* ovf_l = nullptr;
@@ -318,9 +395,11 @@ struct BuildBuffers {
     unsigned long long* counters = nullptr;   // [0] inserted, [1] spill buckets, [2] removed
     void free_temp() {
         cudaFree(cnt8); cudaFree(ovf_c); cudaFree(ovf_l); cudaFree(flags); cudaFree(counters);
+        cudaFree(ovf_cnt8); cudaFree(del_main); cudaFree(del_ovf);
         cnt8 = nullptr; ovf_c = nullptr; ovf_l = nullptr; flags = nullptr; counters = nullptr;
+        ovf_cnt8 = nullptr; del_main = nullptr; del_ovf = nullptr;
     }
-    void free_all() { free_temp(); cudaFree(table); table = nullptr; }
+    void free_all() { free_temp(); cudaFree(table); cudaFree(ovf); table = nullptr; ovf = nullptr; }
 };
 
 int alloc_build(const Geometry& g, uint64_t n_expected, BuildBuffers& b, BuildCtx& x, uint64_t htsize) {
@@ -352,30 +431,53 @@ int finish_build(cuclark_db* db, const Geometry& g, BuildBuffers& b, BuildCtx& x
     uint32_t flags[2];
     CK(cudaMemcpy(flags, b.flags, 8, cudaMemcpyDeviceToHost));
     if (flags[1]) { set_error("table build: bucket counter/overflow-list exhausted (flags %u)", flags[1]); return CUCLARK_ERR_BUILD; }
-    const uint32_t n_ovf = flags[0];
-    if (n_ovf) {
-        if (g.layout == LAYOUT_NARROW) k_place_spills<LAYOUT_NARROW><<<(n_ovf + 255) / 256, 256>>>(x, n_ovf);
-        else k_place_spills<LAYOUT_WIDE><<<(n_ovf + 255) / 256, 256>>>(x, n_ovf);
+    const uint32_t n_ovf_entries = flags[0];
+    uint64_t n_ovf = 0;
+    if (n_ovf_entries) {
+        n_ovf = (uint64_t)((double)n_ovf_entries / OVF_LOAD) + 64;
+        if (cudaMalloc(&b.ovf, n_ovf * 32) != cudaSuccess) { cudaGetLastError(); set_error("cudaMalloc of overflow table failed"); return CUCLARK_ERR_NOMEM; }
+        CK(cudaMalloc(&b.ovf_cnt8, (n_ovf / 4 + 1) * 4));
+        CK(cudaMemset(b.ovf_cnt8, 0, (n_ovf / 4 + 1) * 4));
+        k_init_table<<<(unsigned)((2 * n_ovf + 255) / 256), 256>>>(b.ovf, n_ovf, LAYOUT_WIDE);
+        CK(cudaGetLastError());
+        x.ovf = b.ovf; x.ovf_cnt8 = b.ovf_cnt8; x.n_ovf = n_ovf;
+        k_place_spills<<<(n_ovf_entries + 255) / 256, 256>>>(x, n_ovf_entries);
         CK(cudaGetLastError());
     }
     if (dedupe) {
-        const unsigned blocks = (unsigned)((g.n_local + 255) / 256);
-        if (g.layout == LAYOUT_NARROW) k_dedupe<LAYOUT_NARROW><<<blocks, 256>>>(b.table, g.n_local, b.counters + 2);
-        else k_dedupe<LAYOUT_WIDE><<<blocks, 256>>>(b.table, g.n_local, b.counters + 2);
+        CK(cudaMalloc(&b.del_main, g.n_local));
+        CK(cudaMalloc(&b.del_ovf, n_ovf + 1));
+        const unsigned blocks = (unsigned)((std::max(g.n_local, n_ovf) + 255) / 256);
+        if (g.layout == LAYOUT_NARROW) {
+            DedupeView<LAYOUT_NARROW> v{b.table, b.ovf, g.M, g.lo, g.n_local, n_ovf, b.del_main, b.del_ovf};
+            k_dedupe_main<LAYOUT_NARROW><<<(unsigned)((g.n_local + 255) / 256), 256>>>(v);
+            if (n_ovf) k_dedupe_ovf<LAYOUT_NARROW><<<(unsigned)((n_ovf + 255) / 256), 256>>>(v, x.magic);
+            else CK(cudaMemset(b.del_ovf, 0, 1));
+            k_dedupe_apply<LAYOUT_NARROW><<<blocks, 256>>>(v, b.counters + 2);
+        } else {
+            DedupeView<LAYOUT_WIDE> v{b.table, b.ovf, g.M, g.lo, g.n_local, n_ovf, b.del_main, b.del_ovf};
+            k_dedupe_main<LAYOUT_WIDE><<<(unsigned)((g.n_local + 255) / 256), 256>>>(v);
+            if (n_ovf) k_dedupe_ovf<LAYOUT_WIDE><<<(unsigned)((n_ovf + 255) / 256), 256>>>(v, x.magic);
+            else CK(cudaMemset(b.del_ovf, 0, 1));
+            k_dedupe_apply<LAYOUT_WIDE><<<blocks, 256>>>(v, b.counters + 2);
+        }
         CK(cudaGetLastError());
     }
     k_table_stats<<<(unsigned)((g.n_local + 255) / 256), 256>>>(b.table, g.n_local, b.counters + 1);
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(flags, b.flags, 8, cudaMemcpyDeviceToHost));
-    if (flags[1]) { set_error("table build: no free slot within %d buckets of home (flags %u)", MAX_DISP, flags[1]); return CUCLARK_ERR_BUILD; }
+    if (flags[1]) { set_error("table build: overflow table full (flags %u)", flags[1]); return CUCLARK_ERR_BUILD; }
     unsigned long long counters[3];
     CK(cudaMemcpy(counters, b.counters, 24, cudaMemcpyDeviceToHost));
     db->n_entries = counters[0] - counters[2];
-    db->n_spilled = n_ovf;
+    db->n_spilled = n_ovf_entries;
     db->n_spill_buckets = counters[1];
     db->d_table = b.table;
+    db->d_ovf = b.ovf;
     db->view.buckets = b.table;
+    db->view.ovf = b.ovf;
+    db->view.n_ovf = n_ovf;
     db->view.M = g.M;
     db->view.magic = x.magic;
     db->view.lo = g.lo;
@@ -390,7 +492,9 @@ int finish_build(cuclark_db* db, const Geometry& g, BuildBuffers& b, BuildCtx& x
 
 void table_free(cuclark_db* db) {
     if (db->d_table) cudaFree(db->d_table);
+    if (db->d_ovf) cudaFree(db->d_ovf);
     db->d_table = nullptr;
+    db->d_ovf = nullptr;
     db->view = TableView{};
     db->n_entries = db->n_spilled = db->n_spill_buckets = 0;
 }

@@ -132,7 +132,8 @@ def stage_csv(names, outdir):
             if not os.path.exists(csv):
                 print(name, "reference produced no CSV; see log")
                 continue
-            with open(csv, "rb") as f, gzip.open(os.path.join(outdir, f"{name}.csv.gz"), "wb", mtime=0) as g:
+            with open(csv, "rb") as f, open(os.path.join(outdir, f"{name}.csv.gz"), "wb") as raw, \
+                    gzip.GzipFile(filename="", mode="wb", fileobj=raw, mtime=0) as g:
                 shutil.copyfileobj(f, g)
             print(name, "csv bytes", os.path.getsize(csv))
         finally:

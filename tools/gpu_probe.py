@@ -33,7 +33,7 @@ for T in targets_list:
     r.update({kk: st[kk] for kk in ("n_entries", "n_buckets", "table_bytes", "n_spilled", "n_spill_buckets", "layout")})
     # gather ceiling
     probes = 1 << 28
-    for B in (32, 64, 128):
+    for B in ((32, 64, 128) if os.environ.get("PROBE_ALL") else (32,)):
         for ilp in (1, 4, 8):
             ms = g.gather_bench(probes, B, ilp, 3)
             r[f"gather_{B}B_ilp{ilp}_Gps"] = probes / ms / 1e6
@@ -47,15 +47,17 @@ for T in targets_list:
     for pct_random in (10, 100):
         g.synth_reads_device(2, 1, T, 4_000_000, 0, n_reads, L, pct_random, 0, d_ptr.data_ptr(), d_cont.data_ptr())
         g.stats(sync=True)
-        stream = torch.cuda.current_stream().cuda_stream
+        ts = torch.cuda.Stream()          # a real handle: 0/NULL would mean "library stream"
+        torch.cuda.synchronize()
+        stream = ts.cuda_stream
         for rows in (0, 1):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             for it in range(4):
                 if it == 1:
-                    e0.record()
+                    e0.record(ts)
                 g.classify_device(d_ptr.data_ptr(), d_cont.data_ptr(), n_reads, d_final.data_ptr(),
                                   d_rows.data_ptr() if rows else 0, stream)
-            e1.record()
+            e1.record(ts)
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / 3
             s2 = g.stats(sync_stream=stream, sync=True)
