@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""bench.py — k-mer lookups/s and reads/s of the classification hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Workload (BASELINE.json configs[1], the configuration the metric is quoted on):
+cuCLARK full variant, k=31, synthetic bacterial-scale database of 1,430 targets x
+4 Mbp = 5.72 G target-specific 31-mers (~36 GB in the reference's .sz/.ky/.lb
+form; ~77 GB as 32-byte sector buckets in HBM), 10 M single-end 150 bp reads
+(90 % sampled from the targets, 10 % random). A step = one pass of the hot path
+(k-mer extraction, table probe, per-read histogram, top-2) over the 10 M reads.
+Database and reads are generated ON the device from seeded counter-based hashes
+(cuclark_b200/synth.py is the numpy twin, checked in tests/).
+
+N > 1 (torchrun, one rank per GPU): read-partitioned mode against a replicated
+table, the reads are split over the ranks, no collective on the data path
+("scaling": "weak": every rank classifies --reads reads).
+
+Output: ONE JSON line on rank 0. `value` = lookups/s with inputs resident in HBM;
+`e2e` = the same through the batch API with pinned HOST buffers (H2D of the packed
+reads and D2H of the results inside the timed region); `roofline` for the classify
+kernel (32 algorithmic bytes per lookup); `cpu_baseline` = the oracle port on the
+host cores on a bounded sample (N=1 only).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+K = 31
+GENOME_LEN = 4_000_000
+READ_LEN = 150
+DB_SEED, READ_SEED = 1, 2
+BYTES_PER_LOOKUP = 32          # one sector bucket; SURVEY.md section 8(d), DESIGN.md
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--targets", type=int, default=int(os.environ.get("CUCLARK_BENCH_TARGETS", 1430)))
+    ap.add_argument("--reads", type=int, default=int(os.environ.get("CUCLARK_BENCH_READS", 10_000_000)))
+    ap.add_argument("--pct-random", type=int, default=10)
+    ap.add_argument("--cpu-targets", type=int, default=8, help="targets of the CPU baseline's (smaller) database")
+    ap.add_argument("--cpu-reads", type=int, default=400_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples nvidia-smi clocks and throttle reasons during the timed region."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0])); smax = float(p[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f)["hbm_gbs"], "measured (MEASURED_PEAKS.json: device copy)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(workload_key: str):
+    """dram bytes per classify launch from the committed ncu capture, if any (profiles/traffic.json)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(workload_key)
+    except Exception:
+        return None
+
+
+# ---------------------------------------------------------------- CPU legs (oracle: checker/baseline only)
+def cpu_sample(args, threads: int):
+    """Reads + port database for the CPU legs: a bounded sample of the same workload."""
+    from cuclark_b200 import synth
+    from oracle.binding import HTSIZE_FULL, Oracle
+    orc = Oracle()
+    t0 = time.time()
+    db = orc.db_build_synth(DB_SEED, args.cpu_targets, GENOME_LEN, K, HTSIZE_FULL, 0, threads)
+    build_s = time.time() - t0
+    codes, *_ = synth.read_codes(READ_SEED, args.cpu_reads, READ_LEN, args.cpu_targets, GENOME_LEN, DB_SEED,
+                                 pct_random=args.pct_random)
+    data = synth.reads_fastq(codes)
+    return orc, db, data, build_s
+
+
+def cpu_step(orc, db, data, n_targets, threads):
+    """index + 2-bit pack + extract + lookup + histogram + top-2 on the host; returns (seconds, lookups, reads)."""
+    t0 = time.perf_counter()
+    ix, buf = orc.index(data, threads)
+    ptr, cont = orc.pack(ix, buf, K)
+    final, _, lookups = orc.classify(db, ptr, cont, n_targets, 15, want_rows=False, threads=threads)
+    dt = time.perf_counter() - t0
+    n = ptr.size - 1
+    orc.free_index(ix)
+    return dt, lookups, n
+
+
+def run_reference(args, rank: int):
+    """--impl reference: the reference algorithm on the host cores (the oracle port)."""
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    orc, db, data, build_s = cpu_sample(args, threads)
+    for _ in range(min(args.warmup, 1)):
+        cpu_step(orc, db, data, args.cpu_targets, threads)
+    tot_t = tot_l = tot_r = 0
+    for _ in range(args.steps):
+        dt, lk, n = cpu_step(orc, db, data, args.cpu_targets, threads)
+        tot_t += dt; tot_l += lk; tot_r += n
+    val = tot_l / tot_t
+    sample = (f"{args.cpu_reads} x {READ_LEN} bp reads per step against a {args.cpu_targets} x 4 Mbp "
+              f"({db.size / 1e6:.0f} M 31-mer) database in the reference's table layout (HTSIZE 1610612741); "
+              f"index+pack+extract+lookup+histogram+top-2, OpenMP")
+    line = {
+        "impl": "reference", "metric": "kmer_lookups_per_s", "value": val, "unit": "lookups/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "reads_per_s": tot_r / tot_t,
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": val, "unit": "lookups/s", "cores": threads, "kind": "port", "sample": sample,
+                         "db_build_s": build_s},
+        "e2e": {"value": val, "unit": "lookups/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {"workload": f"config2: cuCLARK k=31, synthetic DB {args.targets} targets x 4 Mbp "
+                        f"(~{args.targets * (GENOME_LEN - K + 1) / 1e9:.2f} G 31-mers), "
+                        f"{args.reads} x {READ_LEN} bp single-end reads per GPU, {args.pct_random}% random",
+            "k": K, "targets": args.targets, "reads_per_gpu": args.reads, "read_len": READ_LEN,
+            "mode": "read-partitioned, replicated table" if world > 1 else "single GPU",
+            "l2_policy": "inputs larger than L2 (packed reads 400 MB, table >> 126 MB); no flush needed"}
+
+
+# ---------------------------------------------------------------- GPU arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from cuclark_b200.api import CuClarkDB, HTSIZE_FULL
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the host baseline)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n, T = args.reads, args.targets
+    g = CuClarkDB(K, T, htsize=HTSIZE_FULL, device=local)
+    t0 = time.time()
+    g.build_synthetic(DB_SEED, T, GENOME_LEN, 0)
+    build_s = time.time() - t0
+    st = g.stats()
+
+    per = 1 + (READ_LEN + 7) // 8
+    d_ptr = torch.empty(n + 1, dtype=torch.int32, device="cuda")
+    d_cont = torch.empty(n * per, dtype=torch.int16, device="cuda")
+    d_final = torch.empty(n * 5, dtype=torch.int16, device="cuda")
+    ts = torch.cuda.Stream()
+    stream = ts.cuda_stream
+    # rank r classifies reads [r*n, (r+1)*n) of the global read set
+    g.synth_reads_device(READ_SEED, DB_SEED, T, GENOME_LEN, rank * n, n, READ_LEN, args.pct_random, 0,
+                         d_ptr.data_ptr(), d_cont.data_ptr(), stream)
+    g.stats(sync_stream=stream, sync=True)
+
+    def step():
+        g.classify_device(d_ptr.data_ptr(), d_cont.data_ptr(), n, d_final.data_ptr(), 0, stream)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    barrier()
+    ev[0].record(ts)
+    for i in range(args.steps):
+        step()
+        ev[i + 1].record(ts)
+    barrier()
+    total_ms = ev[0].elapsed_time(ev[-1])
+    step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    lookups = g.stats(sync_stream=stream, sync=True)["lookups"]
+
+    # ---- e2e: pinned host buffers -> batch API -> host results --------------------
+    e2e = None
+    if not args.no_e2e:
+        nb = 16
+        bn = (n + nb - 1) // nb
+        h_ptr = d_ptr.cpu().numpy().view(np.uint32)
+        h_cont = d_cont.cpu().numpy().view(np.uint16)
+        # the caller's packed reads live in the library's pinned buffers (as the reference's pack
+        # loop writes them, src/CuCLARK_hh.hh:1616-1708); filled once, outside the timed region
+        views = g.malloc(nb, bn, bn * per, is_extended=False)
+        spans = []
+        for b in range(nb):
+            lo, hi = b * bn, min(n, (b + 1) * bn)
+            m = hi - lo
+            vp, vc, _, _ = views[b]
+            np.subtract(h_ptr[lo:hi + 1], h_ptr[lo], out=vp[:m + 1])
+            vc[:m * per] = h_cont[lo * per:hi * per]
+            spans.append((lo, hi))
+
+        def e2e_pass():
+            for b, (lo, hi) in enumerate(spans):
+                g.readyBatch(b, hi - lo, (hi - lo) * per)
+                g.queryBatch(b)                      # async: H2D + kernels + D2H on the batch's stream
+            for b in range(nb):
+                g.waitForBatch(b)                    # results are now in pinned host memory
+
+        e2e_pass()
+        barrier()
+        t0 = time.perf_counter()
+        reps = max(2, min(args.steps, 4))
+        for _ in range(reps):
+            e2e_pass()
+        barrier()
+        e2e_s = (time.perf_counter() - t0) / reps
+        out = np.concatenate([views[b][2][:hi - lo] for b, (lo, hi) in enumerate(spans)])
+        same = bool(np.array_equal(out, d_final.view(n, 5).cpu().numpy().view(np.uint16)))
+        g.freeBatchMemory()
+        e2e = {"s": e2e_s, "same_as_device_path": same,
+               "h2d": int((n + nb) * 4 + n * per * 2), "d2h": int(n * 10 + nb * 32)}
+    clocks = sampler.stop()
+
+    # ---- roofline denominator measured on the same table ---------------------------
+    gather_ms = min(g.gather_bench(1 << 28, 32, ilp, 3) for ilp in (4, 8))
+    random_gbs = (1 << 28) * 32 / gather_ms / 1e6
+
+    # ---- size-independent property check at full size ------------------------------
+    f = d_final.view(n, 5).cpu().numpy().view(np.uint16)
+    classified = float((f[:, 1] > 0).mean())
+    full_hits = float((f[:, 2] == READ_LEN - K + 1).mean())
+
+    # ---- reduce over ranks --------------------------------------------------------
+    t = torch.tensor([total_ms, e2e["s"] if e2e else 0.0], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([float(lookups), float(n)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    total_ms_max, e2e_s_max = t.tolist()
+    lookups_all, reads_all = cnt.tolist()
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        kernel_ms = float(np.mean(step_ms))
+        achieved = lookups * BYTES_PER_LOOKUP / (kernel_ms * 1e-3) / 1e9
+        value = lookups_all * args.steps / (total_ms_max * 1e-3)
+        line = {
+            "metric": "kmer_lookups_per_s", "value": value, "unit": "lookups/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "reads_per_s": reads_all * args.steps / (total_ms_max * 1e-3),
+            "config": workload_config(args, world),
+            "table": {"entries": st["n_entries"], "buckets": st["n_buckets"], "bytes": st["table_bytes"],
+                      "layout": "narrow" if st["layout"] == 1 else "wide", "overflow_entries": st["n_spilled"],
+                      "overflowed_buckets": st["n_spill_buckets"], "build_s": build_s},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": ncu_traffic("config2"), "peak_source": peak_src,
+                         "kernel": "k_classify<NARROW,false>", "kernel_ms": kernel_ms,
+                         "bytes_per_lookup": BYTES_PER_LOOKUP, "lookups_per_launch": lookups,
+                         "random_access_peak": random_gbs, "frac_random_access": achieved / random_gbs,
+                         "random_access_peak_source": "measured live: 2^28 random 32 B sector loads over the same table"},
+            "clocks": clocks,
+            "gpu_launches": args.steps * 3,   # memset + k_classify + k_classify_dense per step
+            "parity_properties": {"classified_frac": classified, "expected_classified_frac": 1 - args.pct_random / 100,
+                                  "reads_with_all_kmers_hit_frac": full_hits},
+        }
+        if e2e:
+            line["e2e"] = {"value": lookups_all / e2e_s_max, "unit": "lookups/s", "reads_per_s": reads_all / e2e_s_max,
+                           "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
+                           "ms_per_step": e2e_s_max * 1e3, "results_equal_device_path": e2e["same"],
+                           "path": "pinned host packed reads -> cuclark_batch_query (H2D, kernels, D2H) -> host results"}
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            orc, db, data, cpu_build_s = cpu_sample(args, threads)
+            dt, lk, nr = cpu_step(orc, db, data, args.cpu_targets, threads)
+            line["cpu_baseline"] = {
+                "value": lk / dt, "unit": "lookups/s", "cores": threads, "kind": "port",
+                "reads_per_s": nr / dt, "db_build_s": cpu_build_s,
+                "sample": f"{args.cpu_reads} x {READ_LEN} bp reads against a {args.cpu_targets} x 4 Mbp "
+                          f"({db.size / 1e6:.0f} M 31-mer) database in the reference's table layout; "
+                          f"index+pack+extract+lookup+histogram+top-2 (oracle port, OpenMP)"}
+        print(json.dumps(line), flush=True)
+    g.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a, int(os.environ.get("RANK", 0)))
+    else:
+        run_b200(a)

@@ -107,6 +107,9 @@ class Oracle:
         lib.orc_db_from_arrays.argtypes = [u64, C.c_int, C.c_int, P(u8), C.c_void_p, P(u16), C.c_int]
         lib.orc_db_load.restype = C.c_void_p
         lib.orc_db_load.argtypes = [C.c_char_p, u64, C.c_int, C.c_int, C.c_int]
+        lib.orc_db_build_synth.restype = C.c_void_p
+        lib.orc_db_build_synth.argtypes = [C.c_uint32, C.c_uint32, u64, C.c_int, u64, C.c_int, C.c_int, C.c_int,
+                                           C.c_char_p]
         lib.orc_db_free.argtypes = [C.c_void_p]
         lib.orc_db_size.restype = u64
         lib.orc_db_size.argtypes = [C.c_void_p]
@@ -148,6 +151,12 @@ class Oracle:
         kb = ky.dtype.itemsize
         ky = np.ascontiguousarray(ky)
         h = self.lib.orc_db_from_arrays(htsize, k, kb, _p(sz, C.c_uint8), ky.ctypes.data, _p(lb, C.c_uint16), sfactor)
+        return OracleDB(self.lib, h, htsize, k)
+
+    def db_build_synth(self, seed: int, n_targets: int, genome_len: int, k: int, htsize: int, light_gap: int = 0,
+                       threads: int = 1, write_base: str | None = None) -> OracleDB:
+        h = self.lib.orc_db_build_synth(seed, n_targets, genome_len, k, htsize, key_bytes_for(k, htsize), light_gap,
+                                        threads, write_base.encode() if write_base else None)
         return OracleDB(self.lib, h, htsize, k)
 
     def canonical(self, kmer: int, k: int) -> int:

@@ -120,6 +120,117 @@ orc_db* orc_db_load(const char* base, uint64_t htsize, int k, int key_bytes, int
     return db;
 }
 
+/* ---- synthetic genomes: twin of cuclark_b200/synth.py (mix64/_key/genome word) ---- */
+static uint64_t mix64(uint64_t x) {
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+static uint64_t synth_key(uint64_t tag, uint32_t seed, uint64_t a, uint64_t b) {
+    uint64_t h = mix64((tag << 56) ^ ((uint64_t)(seed & 0xFFFFu) << 40) ^ b);
+    return mix64(h ^ (a * 0x9E3779B97F4A7C15ull));
+}
+static unsigned synth_base(uint32_t seed, uint32_t t, uint64_t p) {
+    return (unsigned)(synth_key(0x47, seed, t, p >> 5) >> (2 * (p & 31))) & 3u;
+}
+
+typedef struct { uint64_t key; uint16_t label; } kl_t;
+
+static void radix_sort_kl(kl_t* a, kl_t* tmp, size_t n) {
+    for (int pass = 0; pass < 8; pass++) {
+        size_t cnt[257] = {0};
+        int sh = 8 * pass;
+        for (size_t i = 0; i < n; i++) cnt[((a[i].key >> sh) & 0xFF) + 1]++;
+        if (cnt[1] == n) continue;                 /* byte is all zero */
+        for (int b = 0; b < 256; b++) cnt[b + 1] += cnt[b];
+        for (size_t i = 0; i < n; i++) tmp[cnt[(a[i].key >> sh) & 0xFF]++] = a[i];
+        memcpy(a, tmp, n * sizeof(kl_t));
+    }
+}
+
+/* Builder semantics: src/CuCLARK_hh.hh:694-767 (light scanner), :896-975 (full
+ * scanner), src/HashTableStorage_hh.hh:484-523 (addElement, canonical = min) and
+ * :242-292 (RemoveCommon: keep k-mers of exactly one target); file layout
+ * src/hashTable_hh.hh:591-663. */
+orc_db* orc_db_build_synth(uint32_t seed, uint32_t n_targets, uint64_t genome_len, int k, uint64_t htsize,
+                           int key_bytes, int light_gap, int threads, const char* write_base) {
+    uint64_t per = light_gap > 0 ? ((genome_len / k) + light_gap - 1) / light_gap : genome_len - k + 1;
+    size_t n = (size_t)per * n_targets;
+    kl_t* a = (kl_t*)malloc(n * sizeof(kl_t));
+    kl_t* tmp = (kl_t*)malloc(n * sizeof(kl_t));
+    uint64_t mask = k == 32 ? ~0ull : ((1ull << (2 * k)) - 1);
+#pragma omp parallel for num_threads(threads) schedule(dynamic, 1)
+    for (uint32_t t = 0; t < n_targets; t++) {
+        kl_t* out = a + (size_t)t * per;
+        if (light_gap > 0) {
+            for (uint64_t j = 0; j < per; j++) {
+                uint64_t start = j * (uint64_t)light_gap * k, R = 0;
+                for (int i = 0; i < k; i++) R = (R << 2) | (3u - synth_base(seed, t, start + i));
+                uint64_t c = orc_canonical(R, k);
+                out[j].key = ((c % htsize) << 32) | (c / htsize);     /* needs quotient < 2^32 */
+                out[j].label = (uint16_t)t;
+            }
+        } else {
+            uint64_t R = 0, word = 0;
+            for (uint64_t p = 0; p < genome_len; p++) {
+                if ((p & 31) == 0) word = synth_key(0x47, seed, t, p >> 5);
+                R = ((R << 2) | (3u - ((unsigned)(word >> (2 * (p & 31))) & 3u))) & mask;
+                if (p + 1 >= (uint64_t)k) {
+                    uint64_t c = orc_canonical(R, k);
+                    out[p + 1 - k].key = ((c % htsize) << 32) | (c / htsize);
+                    out[p + 1 - k].label = (uint16_t)t;
+                }
+            }
+        }
+    }
+    radix_sort_kl(a, tmp, n);
+    free(tmp);
+    /* unique + RemoveCommon */
+    size_t m = 0;
+    for (size_t i = 0; i < n;) {
+        size_t j = i + 1;
+        int common = 0;
+        while (j < n && a[j].key == a[i].key) { common |= a[j].label != a[i].label; j++; }
+        if (!common) a[m++] = a[i];
+        i = j;
+    }
+    orc_db* db = (orc_db*)calloc(1, sizeof(orc_db));
+    db->htsize = htsize; db->k = k; db->key_bytes = key_bytes; db->n = m;
+    db->start = (uint64_t*)calloc(htsize + 1, sizeof(uint64_t));
+    db->keys = (uint64_t*)malloc((m ? m : 1) * sizeof(uint64_t));
+    db->labels = (uint16_t*)malloc((m ? m : 1) * sizeof(uint16_t));
+    for (size_t i = 0; i < m; i++) {
+        db->start[(a[i].key >> 32) + 1]++;
+        db->keys[i] = a[i].key & 0xFFFFFFFFull;
+        db->labels[i] = a[i].label;
+    }
+    free(a);
+    if (write_base) {
+        size_t L = strlen(write_base) + 8;
+        char* p = (char*)malloc(L);
+        uint8_t* sz = (uint8_t*)malloc(htsize);
+        for (uint64_t r = 0; r < htsize; r++) sz[r] = (uint8_t)db->start[r + 1];
+        snprintf(p, L, "%s.sz", write_base);
+        FILE* f = fopen(p, "wb"); if (f) { fwrite(sz, 1, htsize, f); fclose(f); }
+        free(sz);
+        snprintf(p, L, "%s.ky", write_base);
+        f = fopen(p, "wb");
+        if (f) {
+            for (size_t i = 0; i < m; i++) {
+                if (key_bytes == 4) { uint32_t v = (uint32_t)db->keys[i]; fwrite(&v, 4, 1, f); }
+                else if (key_bytes == 2) { uint16_t v = (uint16_t)db->keys[i]; fwrite(&v, 2, 1, f); }
+                else fwrite(&db->keys[i], 8, 1, f);
+            }
+            fclose(f);
+        }
+        snprintf(p, L, "%s.lb", write_base);
+        f = fopen(p, "wb"); if (f) { fwrite(db->labels, 2, m, f); fclose(f); }
+        free(p);
+    }
+    for (uint64_t r = 0; r < htsize; r++) db->start[r + 1] += db->start[r];
+    return db;
+}
+
 void orc_db_free(orc_db* db) {
     if (!db) return;
     free(db->start); free(db->keys); free(db->labels); free(db);
@@ -397,11 +508,14 @@ uint64_t orc_classify(const orc_db* db, const uint32_t* reads_ptr, const uint16_
                 unsigned L = cont[p++];
                 const uint16_t* c = cont + p;
                 p += (L - 1) / 8 + 1;
-                for (size_t w = 0; w + (size_t)k <= L; w++) {
+                /* rolling form of part_kmer(): same windows, same integers */
+                uint64_t R = 0, mask = k == 32 ? ~0ull : ((1ull << (2 * k)) - 1);
+                for (size_t q = 0; q < L; q++) {
+                    R = ((R << 2) | ((c[q >> 3] >> (2 * (7 - (q & 7)))) & 3u)) & mask;
+                    if (q + 1 < (size_t)k) continue;
                     uint16_t lab;
                     lookups++;
-                    if (orc_db_find(db, part_kmer(c, w, k), part_lo, part_hi, &lab) && lab < n_targets)
-                        hits[lab]++;
+                    if (orc_db_find(db, R, part_lo, part_hi, &lab) && lab < n_targets) hits[lab]++;
                 }
             }
             top2_scan(hits, n_targets, final5 + 5 * r);
