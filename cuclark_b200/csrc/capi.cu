@@ -11,6 +11,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "internal.h"
@@ -116,6 +117,15 @@ int cuclark_create(const cuclark_config* cfg, cuclark_db** out) {
     if (db->row_pairs > 63) { delete db; set_error("row_pairs must be <= 63"); return CUCLARK_ERR_ARG; }
     int rc = use_device(db);
     if (rc) { delete db; return rc; }
+    // A probe needs ONE 32-byte sector; by default the L2 fetches the whole 128-byte line from
+    // HBM on a sector miss, which quadruples DRAM traffic for random probes (ncu:
+    // dram__bytes_read = 132 B per lookup). Ask for sector-granular fetches.
+    {
+        size_t gran = 32;
+        if (const char* e = getenv("CUCLARK_L2_FETCH")) gran = (size_t)atoi(e);
+        if (gran == 32 || gran == 64 || gran == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
+        cudaGetLastError();
+    }
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) { delete db; set_error("cudaGetDeviceProperties failed"); return CUCLARK_ERR_CUDA; }
     db->sm_count = prop.multiProcessorCount;

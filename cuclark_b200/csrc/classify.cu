@@ -33,6 +33,7 @@ constexpr int ILP_ROUNDS = 4;         // independent probes per lane
 constexpr int CHUNK_ROUNDS = 31;      // rounds of 32 k-mers served by one set of 32 words
 constexpr int MAX_ROW_PAIRS = 63;
 constexpr uint32_t EMPTY = 0xFFFFFFFFu;
+constexpr int COUNTER_CHUNK = 4;      // dynamic work counter (reset with the other counters)
 
 struct ClassifyParams {
     TableView t;
@@ -66,6 +67,24 @@ __device__ __forceinline__ bool tab_add(uint32_t* tkey, uint32_t* tcnt, uint32_t
     return false;
 }
 
+// 64-bit words (32 nt each, MSB first) of up to 128 consecutive containers held as four
+// 32-lane windows: lane j gets containers 4j..4j+3. Only the first nwin windows are live.
+__device__ __forceinline__ uint64_t assemble_words(const uint32_t (&wv)[4], int nwin, int lane) {
+    uint64_t W = 0;
+    const int src = 4 * (lane & 7);
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+        if (u < nwin) {                                   // warp-uniform
+            uint64_t w = 0;
+#pragma unroll
+            for (int t = 0; t < 4; t++)
+                w |= (uint64_t)__shfl_sync(0xFFFFFFFFu, wv[u], src + t) << (48 - 16 * t);
+            if ((lane >> 3) == u) W = w;
+        }
+    }
+    return W;
+}
+
 template <int LAYOUT, bool ROWS>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_classify(const ClassifyParams p) {
     __shared__ uint32_t s_key[WARPS_PER_BLOCK][TSLOTS];
@@ -82,78 +101,114 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_classify(const Classif
     const TableView& T = p.t;
     const int k = T.k;
     const int kshift = 64 - 2 * k;
-    const uint32_t n_warps = gridDim.x * WARPS_PER_BLOCK;
     const int pitch = 2 * p.row_pairs + 2;
     unsigned long long my_lookups = 0;
 
-    for (uint32_t read = blockIdx.x * WARPS_PER_BLOCK + wib; read < p.n_reads; read += n_warps) {
-        uint32_t pos = p.reads_ptr[read];
-        const uint32_t end = p.reads_ptr[read + 1];
-        uint32_t first_label = NO_LABEL, first_cnt = 0, total = 0;
-        bool table_mode = false, overflow = false;
+    // Each warp pulls chunks of 32 consecutive reads from a global counter (dynamic
+    // balance); one coalesced load fetches the chunk's 33 container offsets.
+    for (;;) {
+        uint32_t chunk = 0;
+        if (lane == 0) chunk = atomicAdd(&p.counters[COUNTER_CHUNK], 1u);
+        chunk = __shfl_sync(0xFFFFFFFFu, chunk, 0);
+        const uint64_t base64 = (uint64_t)chunk * 32;
+        if (base64 >= p.n_reads) break;
+        const uint32_t base = (uint32_t)base64;
+        const uint32_t nr = min(32u, p.n_reads - base);
+        const uint32_t my_ptr = p.reads_ptr[min(base + lane, p.n_reads)];
+        const uint32_t last_ptr = p.reads_ptr[min(base + 32u, p.n_reads)];
 
-        while (pos < end) {
-            const uint32_t L = p.cont[pos];
-            const uint32_t first = pos + 1;
-            pos = first + ((L + 7) >> 3);
-            const int nk = (int)L - k + 1;
-            for (int cb = 0; cb < nk; cb += 32 * CHUNK_ROUNDS) {
-                // lane j: nucleotides [cb + 32j, cb + 32j + 32) of the part, MSB first
-                uint64_t W = 0;
-                {
-                    const uint32_t ci = first + (cb >> 3) + 4 * lane;
+        // prefetched first header + first 32-container window of the next read
+        uint32_t pf_hdr = 0, pf_win = 0;
+        {
+            const uint32_t p0 = __shfl_sync(0xFFFFFFFFu, my_ptr, 0), e0 = nr > 1 ? __shfl_sync(0xFFFFFFFFu, my_ptr, 1) : last_ptr;
+            if (p0 < e0) pf_hdr = p.cont[p0];
+            if (p0 + 1 + lane < e0) pf_win = p.cont[p0 + 1 + lane];
+        }
+
+        for (uint32_t ri = 0; ri < nr; ri++) {
+            const uint32_t read = base + ri;
+            uint32_t pos = __shfl_sync(0xFFFFFFFFu, my_ptr, ri);
+            const uint32_t end = ri + 1 < 32 ? __shfl_sync(0xFFFFFFFFu, my_ptr, (ri + 1) & 31) : last_ptr;
+            const uint32_t cur_hdr = pf_hdr, cur_win = pf_win;
+            if (ri + 1 < nr) {                              // prefetch the next read while this one probes
+                const uint32_t pn = end;
+                const uint32_t en = ri + 2 < 32 ? __shfl_sync(0xFFFFFFFFu, my_ptr, (ri + 2) & 31) : last_ptr;
+                pf_hdr = pn < en ? p.cont[pn] : 0;
+                pf_win = pn + 1 + lane < en ? p.cont[pn + 1 + lane] : 0;
+            }
+            uint32_t first_label = NO_LABEL, first_cnt = 0, total = 0;
+            bool table_mode = false, overflow = false;
+            bool first_part = true;
+
+            while (pos < end) {
+                const uint32_t L = first_part ? cur_hdr : (uint32_t)p.cont[pos];
+                const uint32_t first = pos + 1;
+                const uint32_t ncont = (L + 7) >> 3;
+                pos = first + ncont;                         // start of the next part
+                const int nk = (int)L - k + 1;
+                for (int cb = 0; cb < nk; cb += 32 * CHUNK_ROUNDS) {
+                    // lane j: nucleotides [cb + 32j, cb + 32j + 32) of the part, MSB first
+                    const uint32_t co = (uint32_t)cb >> 3;   // first container of this chunk
+                    const int nwin = (int)min(4u, (ncont - co + 31) >> 5);
+                    uint32_t wv[4];
 #pragma unroll
-                    for (int j = 0; j < 4; j++)
-                        if (ci + j < pos) W |= (uint64_t)p.cont[ci + j] << (48 - 16 * j);
-                }
-                const int rounds = min(CHUNK_ROUNDS, (nk - cb + 31) >> 5);
-                for (int r0 = 0; r0 < rounds; r0 += ILP_ROUNDS) {
-                    uint64_t q[ILP_ROUNDS], lb[ILP_ROUNDS];
-                    Sector sec[ILP_ROUNDS];
-                    bool live[ILP_ROUNDS];
-#pragma unroll
-                    for (int j = 0; j < ILP_ROUNDS; j++) {
-                        const int i = r0 + j;
-                        const uint64_t hi = shfl64(W, i & 31), lo = shfl64(W, (i + 1) & 31);
-                        uint64_t x = lane ? ((hi << (2 * lane)) | (lo >> (64 - 2 * lane))) : hi;
-                        x >>= kshift;
-                        const bool valid = i < rounds && cb + 32 * i + lane < nk;
-                        uint64_t b;
-                        divmod_M(canonical(x, k), T.M, T.magic, q[j], b);
-                        lb[j] = b - T.lo;
-                        live[j] = valid && lb[j] < T.n_local;
-                        my_lookups += valid;
-                        if (live[j]) sec[j] = load_sector(T.buckets + 2 * lb[j]);
+                    for (int u = 0; u < 4; u++) {
+                        const uint32_t ci = first + co + 32 * u + lane;
+                        if (u == 0 && first_part && cb == 0) wv[u] = cur_win;
+                        else wv[u] = (u < nwin && ci < pos) ? (uint32_t)p.cont[ci] : 0u;
                     }
+                    const uint64_t W = assemble_words(wv, nwin, lane);
+                    const int rounds = min(CHUNK_ROUNDS, (nk - cb + 31) >> 5);
+                    for (int r0 = 0; r0 < rounds; r0 += ILP_ROUNDS) {
+                        uint64_t q[ILP_ROUNDS];
+                        uint32_t lb[ILP_ROUNDS];
+                        Sector sec[ILP_ROUNDS];
+                        bool live[ILP_ROUNDS];
 #pragma unroll
-                    for (int j = 0; j < ILP_ROUNDS; j++) {
-                        uint32_t label = NO_LABEL;
-                        if (live[j]) {
-                            label = match_sector<LAYOUT>(sec[j], q[j]);
-                            if (label == NO_LABEL && sector_overflowed(sec[j]))
-                                label = ovf_lookup(T, q[j] * T.M + (lb[j] + T.lo));
-                            if (label >= p.n_targets) label = NO_LABEL;
+                        for (int j = 0; j < ILP_ROUNDS; j++) {
+                            const int i = r0 + j;
+                            const uint64_t hi = shfl64(W, i & 31), lo = shfl64(W, (i + 1) & 31);
+                            uint64_t x = lane ? ((hi << (2 * lane)) | (lo >> (64 - 2 * lane))) : hi;
+                            x >>= kshift;
+                            const bool valid = i < rounds && cb + 32 * i + lane < nk;
+                            uint64_t b;
+                            divmod_M(canonical(x, k), T.M, T.magic, q[j], b);
+                            const uint64_t lb64 = b - T.lo;
+                            lb[j] = (uint32_t)lb64;              // n_local < 2^32 (checked at build)
+                            live[j] = valid && lb64 < T.n_local;
+                            my_lookups += valid;
+                            if (live[j]) sec[j] = load_sector(T.buckets + 2 * (uint64_t)lb[j]);
                         }
-                        const uint32_t hitmask = __ballot_sync(0xFFFFFFFFu, label != NO_LABEL);
-                        if (!hitmask) continue;
-                        total += __popc(hitmask);
-                        if (!table_mode) {
-                            if (first_label == NO_LABEL) first_label = __shfl_sync(0xFFFFFFFFu, label, __ffs(hitmask) - 1);
-                            const uint32_t same = __ballot_sync(0xFFFFFFFFu, label == first_label);
-                            if (same == hitmask) { first_cnt += __popc(same); continue; }
-                            table_mode = true;
-                            if (lane == 0 && first_cnt) tab_add(tkey, tcnt, first_label, first_cnt);
+#pragma unroll
+                        for (int j = 0; j < ILP_ROUNDS; j++) {
+                            uint32_t label = NO_LABEL;
+                            if (live[j]) {
+                                label = match_sector<LAYOUT>(sec[j], q[j]);
+                                if (label == NO_LABEL && sector_overflowed(sec[j]))
+                                    label = ovf_lookup(T, q[j] * T.M + ((uint64_t)lb[j] + T.lo));
+                                if (label >= p.n_targets) label = NO_LABEL;
+                            }
+                            const uint32_t hitmask = __ballot_sync(0xFFFFFFFFu, label != NO_LABEL);
+                            if (!hitmask) continue;
+                            total += __popc(hitmask);
+                            if (!table_mode) {
+                                if (first_label == NO_LABEL) first_label = __shfl_sync(0xFFFFFFFFu, label, __ffs(hitmask) - 1);
+                                const uint32_t same = __ballot_sync(0xFFFFFFFFu, label == first_label);
+                                if (same == hitmask) { first_cnt += __popc(same); continue; }
+                                table_mode = true;
+                                if (lane == 0 && first_cnt) tab_add(tkey, tcnt, first_label, first_cnt);
+                                __syncwarp();
+                            }
+                            const uint32_t grp = __match_any_sync(0xFFFFFFFFu, label);
+                            bool ok = true;
+                            if (label != NO_LABEL && lane == __ffs(grp) - 1) ok = tab_add(tkey, tcnt, label, __popc(grp));
+                            if (__any_sync(0xFFFFFFFFu, !ok)) overflow = true;
                             __syncwarp();
                         }
-                        const uint32_t grp = __match_any_sync(0xFFFFFFFFu, label);
-                        bool ok = true;
-                        if (label != NO_LABEL && lane == __ffs(grp) - 1) ok = tab_add(tkey, tcnt, label, __popc(grp));
-                        if (__any_sync(0xFFFFFFFFu, !ok)) overflow = true;
-                        __syncwarp();
                     }
                 }
+                first_part = false;
             }
-        }
 
         // ---- per-read result --------------------------------------------------
         uint16_t* row = ROWS ? p.rows + (size_t)read * pitch : nullptr;
@@ -220,7 +275,8 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_classify(const Classif
             const uint32_t v = lane == 0 ? v_sum : lane == 1 ? v_i1 : lane == 2 ? v_h1 : lane == 3 ? v_i2 : v_h2;
             p.final5[(size_t)read * 5 + lane] = (uint16_t)v;
         }
-    }
+        }   // reads of the chunk
+    }       // chunks
     // one atomic per warp
     for (int o = 16; o; o >>= 1) my_lookups += __shfl_xor_sync(0xFFFFFFFFu, my_lookups, o);
     if (lane == 0 && my_lookups)

@@ -93,7 +93,9 @@ struct Sector { uint32_t w[8]; };
 
 __device__ __forceinline__ Sector load_sector(const uint4* p) {
     Sector s;
-    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+    // .L2::64B: on B200 a plain sector miss fills the whole 128-byte line from HBM (ncu: 128 B of
+    // DRAM reads per probe); with this qualifier the fill is 64 B, the smallest the ISA offers.
+    asm volatile("ld.global.nc.L1::no_allocate.L2::64B.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(s.w[0]), "=r"(s.w[1]), "=r"(s.w[2]), "=r"(s.w[3]),
                    "=r"(s.w[4]), "=r"(s.w[5]), "=r"(s.w[6]), "=r"(s.w[7])
                  : "l"(p));

@@ -379,7 +379,7 @@ Geometry choose_geometry(const cuclark_config& cfg, uint64_t n_entries, double g
     g.lo = (uint64_t)((__uint128_t)g.M * i / G);
     const uint64_t hi = (uint64_t)((__uint128_t)g.M * (i + 1) / G);
     g.n_local = hi - g.lo;
-    return g;
+    return g;   // callers check n_local < 2^32 (the classify kernel keeps local bucket ids in 32 bit)
 }
 
 struct BuildBuffers {
@@ -403,6 +403,7 @@ struct BuildBuffers {
 };
 
 int alloc_build(const Geometry& g, uint64_t n_expected, BuildBuffers& b, BuildCtx& x, uint64_t htsize) {
+    if (g.n_local >= 0xFFFFFFFFull) { set_error("shard of %llu buckets exceeds 2^32: use more shards", (unsigned long long)g.n_local); return CUCLARK_ERR_ARG; }
     const uint64_t G = 1;
     (void)G;
     uint64_t ovf_cap64 = n_expected / 6 + (1u << 16);
