@@ -122,11 +122,12 @@ def measured_peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(workload_key: str):
-    """dram bytes per classify launch from the committed ncu capture, if any (profiles/traffic.json)."""
+def ncu_traffic(workload_key: str, lookups: int):
+    """DRAM bytes per classify launch: bytes/lookup from the committed `ncu --set full` capture
+    (profiles/traffic.json) x the lookups of one launch. None if no capture is committed."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            return json.load(f).get(workload_key)
+            return json.load(f)[workload_key]["dram_bytes_per_lookup"] * lookups
     except Exception:
         return None
 
@@ -328,7 +329,7 @@ def run_b200(args):
                       "layout": "narrow" if st["layout"] == 1 else "wide", "overflow_entries": st["n_spilled"],
                       "overflowed_buckets": st["n_spill_buckets"], "build_s": build_s},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic("config2"), "peak_source": peak_src,
+                         "traffic": ncu_traffic("config2", lookups), "algorithmic_bytes": lookups * BYTES_PER_LOOKUP, "peak_source": peak_src,
                          "kernel": "k_classify<NARROW,false>", "kernel_ms": kernel_ms,
                          "bytes_per_lookup": BYTES_PER_LOOKUP, "lookups_per_launch": lookups,
                          "random_access_peak": random_gbs, "frac_random_access": achieved / random_gbs,
