@@ -57,6 +57,8 @@ def parse():
     ap.add_argument("--cpu-reads", type=int, default=400_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--mode", default="read", choices=["read", "table"],
+                    help="multi-GPU mode: read-partitioned/replicated table, or table-partitioned + NCCL row exchange")
     return ap.parse_args()
 
 
@@ -194,7 +196,9 @@ def workload_config(args, world):
                         f"(~{args.targets * (GENOME_LEN - K + 1) / 1e9:.2f} G 31-mers), "
                         f"{args.reads} x {READ_LEN} bp single-end reads per GPU, {args.pct_random}% random",
             "k": K, "targets": args.targets, "reads_per_gpu": args.reads, "read_len": READ_LEN,
-            "mode": "read-partitioned, replicated table" if world > 1 else "single GPU",
+            "mode": ("single GPU" if world == 1 else
+                     "table-partitioned, rows exchanged over NCCL all-to-all" if args.mode == "table"
+                     else "read-partitioned, replicated table"),
             "l2_policy": "inputs larger than L2 (packed reads 400 MB, table >> 126 MB); no flush needed"}
 
 
@@ -219,7 +223,8 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     n, T = args.reads, args.targets
-    g = CuClarkDB(K, T, htsize=HTSIZE_FULL, device=local)
+    table_mode = args.mode == "table" and world > 1
+    g = CuClarkDB(K, T, htsize=HTSIZE_FULL, device=local, shard=(rank, world) if table_mode else (0, 1))
     t0 = time.time()
     g.build_synthetic(DB_SEED, T, GENOME_LEN, 0)
     build_s = time.time() - t0
@@ -236,8 +241,25 @@ def run_b200(args):
                          d_ptr.data_ptr(), d_cont.data_ptr(), stream)
     g.stats(sync_stream=stream, sync=True)
 
-    def step():
-        g.classify_device(d_ptr.data_ptr(), d_cont.data_ptr(), n, d_final.data_ptr(), 0, stream)
+    if table_mode:
+        # every rank probes ITS shard for ALL reads; rows of rank r's reads travel to rank r
+        from cuclark_b200 import multigpu
+        pitch = g.row_size
+        if world * n * per >= 2 ** 32:
+            raise SystemExit("table mode: world*reads*containers exceeds 2^32; lower --reads")
+        all_ptr = (torch.arange(world * n + 1, dtype=torch.int64, device="cuda") * per).to(torch.int32)
+        rows_all = torch.empty((world * n, pitch), dtype=torch.int16, device="cuda")
+
+        def step():
+            with torch.cuda.stream(ts):
+                all_cont = multigpu.gather_fixed_reads(d_cont, world)          # reads to every GPU
+                g.classify_device(all_ptr.data_ptr(), all_cont.data_ptr(), world * n, 0, rows_all.data_ptr(), stream)
+                parts = multigpu.exchange_rows(rows_all, world)                # one all-to-all of sparse rows
+                g.merge_rows_device(parts.data_ptr(), world, n, 0, d_final.data_ptr(), stream)
+                return parts
+    else:
+        def step():
+            g.classify_device(d_ptr.data_ptr(), d_cont.data_ptr(), n, d_final.data_ptr(), 0, stream)
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -254,6 +276,9 @@ def run_b200(args):
     total_ms = ev[0].elapsed_time(ev[-1])
     step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
     lookups = g.stats(sync_stream=stream, sync=True)["lookups"]
+    if table_mode:
+        lookups //= world          # the kernel saw every rank's reads; count each read's k-mers once
+        args.no_e2e = True
 
     # ---- e2e: pinned host buffers -> batch API -> host results --------------------
     e2e = None
