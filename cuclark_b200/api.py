@@ -33,6 +33,7 @@ ABI_SYMBOLS = [
     "cuclark_batch_wait", "cuclark_batches_free",
     "cuclark_classify_host", "cuclark_classify_device", "cuclark_merge_rows_device",
     "cuclark_synth_reads_device", "cuclark_gather_bench",
+    "cuclark_classify_text", "cuclark_classify_file", "cuclark_text_debug",
 ]
 
 
@@ -57,6 +58,29 @@ class Stats(C.Structure):
     def as_dict(self):
         return {f: getattr(self, f) for f, _ in self._fields_}
 
+
+class TextOpts(C.Structure):
+    _fields_ = [("paired", C.c_int), ("extended", C.c_int), ("target_names", C.POINTER(C.c_char_p)),
+                ("chunk_bytes", C.c_size_t), ("n_slots", C.c_int)]
+
+
+class TextStats(C.Structure):
+    _fields_ = [("n_reads", C.c_uint64), ("lookups", C.c_uint64), ("n_containers", C.c_uint64),
+                ("text_bytes", C.c_uint64), ("csv_bytes", C.c_uint64), ("n_chunks", C.c_uint64),
+                ("dense_reads", C.c_uint64), ("truncated_rows", C.c_uint64), ("seconds", C.c_double)]
+
+    def as_dict(self):
+        return {f: getattr(self, f) for f, _ in self._fields_}
+
+
+class TextArrays(C.Structure):
+    _fields_ = [("cap_reads", C.c_size_t), ("cap_containers", C.c_size_t),
+                ("name_s", C.c_void_p), ("name_e", C.c_void_p), ("seq_s", C.c_void_p), ("seq_e", C.c_void_p),
+                ("len", C.c_void_p), ("reads_ptr", C.c_void_p), ("containers", C.c_void_p),
+                ("final5", C.c_void_p), ("rows", C.c_void_p)]
+
+
+SINK_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t)
 
 _lib = None
 
@@ -93,6 +117,9 @@ def load_library():
     lib.cuclark_merge_rows_device.argtypes = [vp, vp, ci, sz, vp, vp, vp]
     lib.cuclark_synth_reads_device.argtypes = [vp, u32, u32, u32, u64, u64, sz, ci, ci, ci, vp, vp, vp]
     lib.cuclark_gather_bench.argtypes = [vp, u64, ci, ci, ci, P(C.c_double)]
+    lib.cuclark_classify_text.argtypes = [vp, vp, sz, P(TextOpts), SINK_FN, vp, P(TextStats)]
+    lib.cuclark_classify_file.argtypes = [vp, C.c_char_p, C.c_char_p, P(TextOpts), P(TextStats)]
+    lib.cuclark_text_debug.argtypes = [vp, vp, sz, P(TextOpts), P(TextArrays), P(TextStats)]
     for name in ABI_SYMBOLS:
         fn = getattr(lib, name)
         if name != "cuclark_last_error":
@@ -262,3 +289,69 @@ class CuClarkDB:
         ms = C.c_double()
         self._check(self._lib.cuclark_gather_bench(self._h, n_probes, bytes_per_probe, ilp, iters, C.byref(ms)))
         return ms.value
+
+    # -- text in, CSV out (CuCLARK::runSimple -> getObjectsDataComputeFullGPU -> printExtendedResultsSynced) ----
+    def _text_opts(self, names, paired, extended, chunk_bytes, n_slots):
+        o = TextOpts()
+        o.paired, o.extended, o.chunk_bytes, o.n_slots = int(paired), int(extended), chunk_bytes, n_slots
+        if names is not None:
+            assert len(names) == self.n_targets
+            arr = (C.c_char_p * len(names))(*[n.encode() for n in names])
+            o.target_names = arr
+            o._keep = arr
+        return o
+
+    def classify_text(self, data, names=None, paired=False, extended=False, chunk_bytes=0, n_slots=0,
+                      out: bytearray | None = None):
+        """Raw FASTA/FASTQ bytes (bytes / numpy uint8 / anything with the buffer protocol, or an int
+        address + length tuple for pinned memory) -> (CSV bytes, stats)."""
+        if isinstance(data, tuple):
+            addr, n = data
+        else:
+            buf = np.frombuffer(data, np.uint8)
+            addr, n = buf.ctypes.data, buf.size
+        o = self._text_opts(names, paired, extended, chunk_bytes, n_slots)
+        chunks = [] if out is None else None
+
+        def sink(_user, ptr, m):
+            piece = C.string_at(ptr, m)
+            if chunks is not None:
+                chunks.append(piece)
+            else:
+                out.extend(piece)
+            return 0
+
+        cb = SINK_FN(sink)
+        st = TextStats()
+        self._check(self._lib.cuclark_classify_text(self._h, addr, n, C.byref(o), cb, None, C.byref(st)))
+        return (b"".join(chunks) if chunks is not None else out), st.as_dict()
+
+    def classify_file(self, objects_path: str, csv_path: str, names=None, paired=False, extended=False,
+                      chunk_bytes=0, n_slots=0) -> dict:
+        o = self._text_opts(names, paired, extended, chunk_bytes, n_slots)
+        st = TextStats()
+        self._check(self._lib.cuclark_classify_file(self._h, objects_path.encode(), csv_path.encode(), C.byref(o),
+                                                     C.byref(st)))
+        return st.as_dict()
+
+    def text_debug(self, data: bytes, max_reads: int, max_containers: int, chunk_bytes=0, n_slots=0,
+                   classify=True, want_rows=False):
+        """Device-side index + pack (+ classify) of raw text; returns the intermediate arrays."""
+        buf = np.frombuffer(data, np.uint8)
+        a = TextArrays()
+        a.cap_reads, a.cap_containers = max_reads, max_containers
+        arrs = {k: np.zeros(max_reads, np.uint64) for k in ("name_s", "name_e", "seq_s", "seq_e", "len")}
+        arrs["reads_ptr"] = np.zeros(max_reads + 1, np.uint32)
+        arrs["containers"] = np.zeros(max_containers, np.uint16)
+        if classify:
+            arrs["final5"] = np.zeros((max_reads, FINAL_ROW), np.uint16)
+            if want_rows:
+                arrs["rows"] = np.zeros((max_reads, self.row_size), np.uint16)
+        for k, v in arrs.items():
+            setattr(a, k, v.ctypes.data)
+        o = self._text_opts(None, False, False, chunk_bytes, n_slots)
+        st = TextStats()
+        self._check(self._lib.cuclark_text_debug(self._h, buf.ctypes.data, buf.size, C.byref(o), C.byref(a), C.byref(st)))
+        n, nc = st.n_reads, st.n_containers
+        out = {k: (v[:n + 1] if k == "reads_ptr" else v[:nc] if k == "containers" else v[:n]) for k, v in arrs.items()}
+        return out, st.as_dict()

@@ -147,6 +147,7 @@ int cuclark_destroy(cuclark_db* db) {
     cudaSetDevice(db->cfg.device);
     cudaDeviceSynchronize();
     free_batches(db);
+    text_pipe_free(db);
     table_free(db);
     free_scratch(db->scratch);
     cudaFree(db->d_dense_hist);

@@ -513,6 +513,7 @@ int classify_launch(cuclark_db* db, const Scratch& sc, const uint32_t* d_ptr, co
     CK(cudaGetLastError());
     // exact fallback; exits at once when the list is empty. Its histogram
     // scratch is shared, so dense kernels are chained across streams.
+    std::lock_guard<std::mutex> dense_guard(db->dense_mu);
     CK(cudaStreamWaitEvent(st, db->dense_chain, 0));
     if (narrow) k_classify_dense<LAYOUT_NARROW><<<db->dense_blocks, 256, 0, st>>>(p, db->d_dense_hist);
     else k_classify_dense<LAYOUT_WIDE><<<db->dense_blocks, 256, 0, st>>>(p, db->d_dense_hist);

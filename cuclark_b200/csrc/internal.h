@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
 #include <vector>
 
 #include "../../include/cuclark_b200.h"
@@ -39,6 +40,8 @@ struct Batch {
     cudaEvent_t done = nullptr;
 };
 
+struct TextPipe;   // stream.cu
+
 }  // namespace cuclark
 
 struct cuclark_db {
@@ -54,6 +57,7 @@ struct cuclark_db {
     cuclark::Scratch scratch;
     uint32_t* d_dense_hist = nullptr;  // dense_blocks * n_targets, shared: dense kernels are
     cudaEvent_t dense_chain = nullptr; //   serialised across streams through this event
+    std::mutex dense_mu;               //   (wait + launch + record must not interleave between host threads)
     int dense_blocks = 0;
     int classify_blocks_per_sm[4] = {0, 0, 0, 0};
     int sm_count = 0;
@@ -66,6 +70,8 @@ struct cuclark_db {
     std::vector<cuclark::Batch> batches;
     size_t batch_max_reads = 0, batch_max_cont = 0;
     bool batch_rows = false;
+    // text pipeline (slots are allocated on first use and kept)
+    cuclark::TextPipe* text_pipe = nullptr;
 };
 
 namespace cuclark {
@@ -84,6 +90,9 @@ int merge_rows_launch(cuclark_db* db, const uint16_t* d_parts, int n_parts, size
 int synth_reads_launch(uint32_t seed, uint32_t genome_seed, uint32_t n_targets, uint64_t genome_len,
                        uint64_t first_read, size_t n_reads, int read_len, int pct_random, int sub_per_10k,
                        uint32_t* d_ptr, uint16_t* d_cont, cudaStream_t st);
+// stream.cu
+void text_pipe_free(cuclark_db* db);
+
 int gather_bench_launch(cuclark_db* db, uint64_t n_probes, int bytes_per_probe, int ilp, int iters, double* ms_out);
 
 }  // namespace cuclark

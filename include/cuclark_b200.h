@@ -43,6 +43,7 @@ extern "C" {
 #define CUCLARK_ERR_NOMEM (-5)
 #define CUCLARK_ERR_STATE (-6)     /* call order violated (no DB loaded, batch not ready, ...) */
 #define CUCLARK_ERR_BUILD (-7)     /* device table could not be built (bucket overflow) */
+#define CUCLARK_ERR_FORMAT (-8)    /* input is neither FASTA nor FASTQ (src/CuCLARK_hh.hh:1535-1538) */
 
 /* reference constants (src/parameters.hh:38-48, src/parameters_light_hh:39-49) */
 #define CUCLARK_HTSIZE_FULL 1610612741ull
@@ -137,6 +138,58 @@ int cuclark_classify_device(cuclark_db* db, const uint32_t* d_reads_ptr, const u
  * Writes merged rows (may be NULL) and final results (may be NULL). */
 int cuclark_merge_rows_device(cuclark_db* db, const uint16_t* d_rows_parts, int n_parts, size_t n_reads,
                               uint16_t* d_rows_out, uint16_t* d_final5, void* stream);
+
+/* ---- text in, CSV out: CuCLARK::getObjectsDataComputeFullGPU + printExtendedResultsSynced --------
+ * (src/CuCLARK_hh.hh:1335-1790 and 1951-2139). The reference indexes reads (:1340-1534) and packs
+ * them (:1616-1708) on the host and prints one CSV line per read with fprintf (:2097-2136). Here
+ * the RAW FASTA/FASTQ bytes are copied to the device in chunks cut at record boundaries and
+ * indexing, 2-bit packing, classification and CSV formatting (including printf's "%g") all run
+ * there; the sink receives the CSV text in file order, starting with the header line. */
+typedef struct cuclark_text_opts {
+    int paired;                        /* Length column = Length - 1: mates joined by one N (:2112)  */
+    int extended;                      /* --extended: one hit-count column per target (:2014-2031)   */
+    const char* const* target_names;   /* n_targets labels in label order (NULL: "T<i>")             */
+    size_t chunk_bytes;                /* text bytes per chunk; 0 = 64 MiB                           */
+    int n_slots;                       /* chunks in flight (host threads, streams); 0 = 4            */
+} cuclark_text_opts;
+
+typedef struct cuclark_text_stats {
+    uint64_t n_reads;
+    uint64_t lookups;
+    uint64_t n_containers;
+    uint64_t text_bytes;               /* H2D payload                                                */
+    uint64_t csv_bytes;                /* D2H payload (+ header)                                     */
+    uint64_t n_chunks;
+    uint64_t dense_reads;
+    uint64_t truncated_rows;
+    double seconds;                    /* wall time of the call                                      */
+} cuclark_text_stats;
+
+/* returns 0 to continue, non-zero to abort (-> CUCLARK_ERR_IO) */
+typedef int (*cuclark_sink_fn)(void* user, const char* data, size_t n);
+
+/* `text` is host memory (pinned memory is copied from directly, pageable memory is staged). */
+int cuclark_classify_text(cuclark_db* db, const uint8_t* text, size_t n, const cuclark_text_opts* opts,
+                          cuclark_sink_fn sink, void* user, cuclark_text_stats* out);
+/* CuCLARK::runSimple (src/CuCLARK_hh.hh:512-573): mmap `objects_path`, write `csv_path`.
+ * CUCLARK_ERR_IO if the input is missing or empty ("Failed to open"). */
+int cuclark_classify_file(cuclark_db* db, const char* objects_path, const char* csv_path,
+                          const cuclark_text_opts* opts, cuclark_text_stats* out);
+
+/* Same pipeline, but instead of CSV text the intermediate arrays come back (host pointers, each
+ * may be NULL): the read index (absolute byte offsets into `text`), the packed reads in the
+ * reference's format, and the per-read results. For parity tests of the device-side stages. */
+typedef struct cuclark_text_arrays {
+    size_t cap_reads;                  /* capacity of the per-read arrays (reads_ptr: +1)            */
+    size_t cap_containers;
+    uint64_t *name_s, *name_e, *seq_s, *seq_e, *len;
+    uint32_t* reads_ptr;
+    uint16_t* containers;
+    uint16_t* final5;
+    uint16_t* rows;
+} cuclark_text_arrays;
+int cuclark_text_debug(cuclark_db* db, const uint8_t* text, size_t n, const cuclark_text_opts* opts,
+                       cuclark_text_arrays* arrays, cuclark_text_stats* out);
 
 /* ---- synthetic reads generated on the device (bench.py): packed format ---- */
 /* Fills d_reads_ptr[n_reads+1] and d_containers (n_reads * (1+ceil(read_len/8)))
