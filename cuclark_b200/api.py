@@ -32,8 +32,9 @@ ABI_SYMBOLS = [
     "cuclark_batches_alloc", "cuclark_batch_buffers", "cuclark_batch_ready", "cuclark_batch_query",
     "cuclark_batch_wait", "cuclark_batches_free",
     "cuclark_classify_host", "cuclark_classify_device", "cuclark_merge_rows_device",
-    "cuclark_synth_reads_device", "cuclark_gather_bench",
+    "cuclark_synth_reads_device", "cuclark_synth_fastq_device", "cuclark_gather_bench",
     "cuclark_classify_text", "cuclark_classify_file", "cuclark_text_debug",
+    "cuclark_classify_text_multi", "cuclark_classify_file_multi", "cuclark_classify_text_buffer",
 ]
 
 
@@ -80,7 +81,7 @@ class TextArrays(C.Structure):
                 ("final5", C.c_void_p), ("rows", C.c_void_p)]
 
 
-SINK_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t)
+SINK_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64)
 
 _lib = None
 
@@ -116,10 +117,14 @@ def load_library():
     lib.cuclark_classify_device.argtypes = [vp, vp, vp, sz, vp, vp, vp]
     lib.cuclark_merge_rows_device.argtypes = [vp, vp, ci, sz, vp, vp, vp]
     lib.cuclark_synth_reads_device.argtypes = [vp, u32, u32, u32, u64, u64, sz, ci, ci, ci, vp, vp, vp]
+    lib.cuclark_synth_fastq_device.argtypes = [vp, u32, u32, u32, u64, u64, sz, ci, ci, ci, vp, vp]
     lib.cuclark_gather_bench.argtypes = [vp, u64, ci, ci, ci, P(C.c_double)]
     lib.cuclark_classify_text.argtypes = [vp, vp, sz, P(TextOpts), SINK_FN, vp, P(TextStats)]
     lib.cuclark_classify_file.argtypes = [vp, C.c_char_p, C.c_char_p, P(TextOpts), P(TextStats)]
     lib.cuclark_text_debug.argtypes = [vp, vp, sz, P(TextOpts), P(TextArrays), P(TextStats)]
+    lib.cuclark_classify_text_multi.argtypes = [P(vp), ci, vp, sz, P(TextOpts), SINK_FN, vp, P(TextStats)]
+    lib.cuclark_classify_text_buffer.argtypes = [P(vp), ci, vp, sz, P(TextOpts), vp, sz, P(sz), P(TextStats)]
+    lib.cuclark_classify_file_multi.argtypes = [P(vp), ci, C.c_char_p, C.c_char_p, P(TextOpts), P(TextStats)]
     for name in ABI_SYMBOLS:
         fn = getattr(lib, name)
         if name != "cuclark_last_error":
@@ -285,6 +290,12 @@ class CuClarkDB:
                                                           n_reads, read_len, pct_random, sub_per_10k, d_ptr, d_cont,
                                                           stream or None))
 
+    def synth_fastq_device(self, seed, genome_seed, n_targets, genome_len, first_read, n_reads, read_len,
+                           pct_random, sub_per_10k, d_text: int, stream: int = 0):
+        self._check(self._lib.cuclark_synth_fastq_device(self._h, seed, genome_seed, n_targets, genome_len, first_read,
+                                                          n_reads, read_len, pct_random, sub_per_10k, d_text,
+                                                          stream or None))
+
     def gather_bench(self, n_probes: int, bytes_per_probe: int = 32, ilp: int = 4, iters: int = 5) -> float:
         ms = C.c_double()
         self._check(self._lib.cuclark_gather_bench(self._h, n_probes, bytes_per_probe, ilp, iters, C.byref(ms)))
@@ -301,30 +312,37 @@ class CuClarkDB:
             o._keep = arr
         return o
 
-    def classify_text(self, data, names=None, paired=False, extended=False, chunk_bytes=0, n_slots=0,
-                      out: bytearray | None = None):
-        """Raw FASTA/FASTQ bytes (bytes / numpy uint8 / anything with the buffer protocol, or an int
-        address + length tuple for pinned memory) -> (CSV bytes, stats)."""
-        if isinstance(data, tuple):
-            addr, n = data
-        else:
-            buf = np.frombuffer(data, np.uint8)
-            addr, n = buf.ctypes.data, buf.size
+    def classify_text(self, data, names=None, paired=False, extended=False, chunk_bytes=0, n_slots=0):
+        """Raw FASTA/FASTQ bytes (anything with the buffer protocol) -> (CSV bytes, stats), through the
+        sink callback (pieces arrive with their byte offset, possibly out of order)."""
+        buf = np.frombuffer(data, np.uint8)
         o = self._text_opts(names, paired, extended, chunk_bytes, n_slots)
-        chunks = [] if out is None else None
+        out = bytearray()
 
-        def sink(_user, ptr, m):
-            piece = C.string_at(ptr, m)
-            if chunks is not None:
-                chunks.append(piece)
-            else:
-                out.extend(piece)
+        def sink(_user, ptr, m, off):
+            if len(out) < off + m:
+                out.extend(bytes(off + m - len(out)))
+            out[off:off + m] = C.string_at(ptr, m)
             return 0
 
         cb = SINK_FN(sink)
         st = TextStats()
-        self._check(self._lib.cuclark_classify_text(self._h, addr, n, C.byref(o), cb, None, C.byref(st)))
-        return (b"".join(chunks) if chunks is not None else out), st.as_dict()
+        self._check(self._lib.cuclark_classify_text(self._h, buf.ctypes.data, buf.size, C.byref(o), cb, None, C.byref(st)))
+        assert len(out) == st.csv_bytes
+        return bytes(out), st.as_dict()
+
+    def classify_text_buffer(self, text_addr: int, n: int, out_addr: int, out_cap: int, names=None, paired=False,
+                             extended=False, chunk_bytes=0, n_slots=0, peers=()):
+        """Host addresses in and out (pinned memory is copied from/to directly). `peers`: more handles
+        (other devices, same database) for a read-partitioned multi-GPU run. Returns (csv_len, stats)."""
+        o = self._text_opts(names, paired, extended, chunk_bytes, n_slots)
+        hs = [self._h] + [p._h for p in peers]
+        arr = (C.c_void_p * len(hs))(*hs)
+        st = TextStats()
+        ln = C.c_size_t()
+        self._check(self._lib.cuclark_classify_text_buffer(arr, len(hs), text_addr, n, C.byref(o), out_addr, out_cap,
+                                                            C.byref(ln), C.byref(st)))
+        return ln.value, st.as_dict()
 
     def classify_file(self, objects_path: str, csv_path: str, names=None, paired=False, extended=False,
                       chunk_bytes=0, n_slots=0) -> dict:

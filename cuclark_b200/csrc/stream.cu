@@ -172,8 +172,6 @@ const char* tp_err_text(uint32_t e) {
 
 // One run over a text buffer, shared by the worker threads.
 struct Job {
-    cuclark_db* db;
-    TextPipe* tp;
     const uint8_t* text;
     size_t n;
     bool fastq, paired, extended, src_pinned;
@@ -185,11 +183,15 @@ struct Job {
     std::condition_variable cv;
     size_t cursor = 0;
     uint64_t next_seq = 0, turn = 0;
+    uint64_t out_off = 0;            // next CSV byte offset (owned by the turn holder)
+    char* out_buf = nullptr;         // optional destination buffer
+    size_t out_cap = 0;
+    bool out_pinned = false;
     bool failed = false;
     int rc = CUCLARK_OK;
     std::string err;
     // totals (guarded by the turn)
-    uint64_t n_reads = 0, n_cont = 0, lookups = 0, csv_bytes = 0, dense = 0, trunc = 0, n_chunks = 0;
+    uint64_t n_reads = 0, n_cont = 0, lookups = 0, dense = 0, trunc = 0, n_chunks = 0;
 
     void fail(int code, const std::string& msg) {
         std::lock_guard<std::mutex> g(mu);
@@ -255,8 +257,8 @@ bool copy_out(Job& J, T* dst, size_t cap, uint64_t at, const void* dsrc, size_t 
     return true;
 }
 
-void worker(Job& J, TextSlot& S) {
-    cuclark_db* db = J.db;
+void worker(Job& J, cuclark_db* db, TextSlot& S) {
+    const TextPipe* tp = db->text_pipe;
     if (cudaSetDevice(db->cfg.device) != cudaSuccess) { J.fail(CUCLARK_ERR_CUDA, "cudaSetDevice failed"); return; }
     const TextSlotDev& d = S.d;
     const int k = db->cfg.k;
@@ -334,81 +336,115 @@ void worker(Job& J, TextSlot& S) {
         }
         // ---- CSV text, in groups that fit the output buffer ----
         const size_t max_line = 39 + (J.extended ? 2 * (size_t)db->cfg.n_targets + 4 * (size_t)db->row_pairs : 0) + 64 +
-                                2 * (size_t)J.tp->names.max_len;
+                                2 * (size_t)tp->names.max_len;
         const uint32_t group = (uint32_t)std::min<size_t>(std::max<size_t>(d.cap_csv / max_line, 1), 0x7FFFFFFF);
+        auto account = [&] {                             // called while holding the turn
+            J.n_reads += n_reads; J.n_cont += n_cont; J.n_chunks++;
+            J.lookups += (uint64_t)S.h_counters[COUNTER_LOOKUPS] | ((uint64_t)S.h_counters[COUNTER_LOOKUPS + 1] << 32);
+            J.dense += S.h_counters[COUNTER_DENSE]; J.trunc += S.h_counters[COUNTER_TRUNC];
+        };
         bool have_turn = false;
         for (uint32_t first = 0; first < n_reads; first += group) {
             const uint32_t cnt = std::min(group, n_reads - first);
-            JRC(tp_csv_launch(d, J.tp->names, first, cnt, k, J.paired, J.extended, db->row_pairs, (uint32_t)db->cfg.n_targets, S.stream));
+            JRC(tp_csv_launch(d, tp->names, first, cnt, k, J.paired, J.extended, db->row_pairs, (uint32_t)db->cfg.n_targets, S.stream));
             JCK(cudaMemcpyAsync(S.h_info, d.info, sizeof(ChunkInfo), cudaMemcpyDeviceToHost, S.stream));
             JCK(cudaStreamSynchronize(S.stream));
             if (S.h_info->err) { J.fail(CUCLARK_ERR_NOMEM, tp_err_text(S.h_info->err)); return; }
+            if (S.h_counters[COUNTER_DENSE] > S.scratch.dense_cap) { J.fail(CUCLARK_ERR_NOMEM, "too many reads needed the dense fallback"); return; }
             const size_t bytes = S.h_info->csv_bytes;
-            if (bytes) {
-                JCK(cudaMemcpyAsync(S.h_csv, d.csv, bytes, cudaMemcpyDeviceToHost, S.stream));
-                JCK(cudaStreamSynchronize(S.stream));
-            }
+            // the turn only hands out the output offset (file order); the copies of different chunks overlap
             if (!have_turn) { if (!wait_turn(J, seq)) return; have_turn = true; }
-            if (bytes && J.sink && J.sink(J.user, S.h_csv, bytes) != 0) {
-                J.fail(CUCLARK_ERR_IO, "the CSV sink reported an error");
-                return;
+            const uint64_t offset = J.out_off;
+            J.out_off += bytes;
+            if (first + cnt >= n_reads) { account(); end_turn(J); }
+            if (!bytes) continue;
+            char* dst = S.h_csv;
+            if (J.out_buf) {
+                if (offset + bytes > J.out_cap) { J.fail(CUCLARK_ERR_NOMEM, "the output buffer is too small for the CSV"); return; }
+                if (J.out_pinned) dst = J.out_buf + offset;
             }
-            J.csv_bytes += bytes;
+            JCK(cudaMemcpyAsync(dst, d.csv, bytes, cudaMemcpyDeviceToHost, S.stream));
+            JCK(cudaStreamSynchronize(S.stream));
+            if (J.out_buf && !J.out_pinned) memcpy(J.out_buf + offset, S.h_csv, bytes);
+            if (J.sink && J.sink(J.user, dst, bytes, offset) != 0) { J.fail(CUCLARK_ERR_IO, "the CSV sink reported an error"); return; }
         }
-        if (!have_turn && !wait_turn(J, seq)) return;
-        if (S.h_counters[COUNTER_DENSE] > S.scratch.dense_cap) { J.fail(CUCLARK_ERR_NOMEM, "too many reads needed the dense fallback"); return; }
-        J.n_reads += n_reads; J.n_cont += n_cont; J.n_chunks++;
-        J.lookups += (uint64_t)S.h_counters[COUNTER_LOOKUPS] | ((uint64_t)S.h_counters[COUNTER_LOOKUPS + 1] << 32);
-        J.dense += S.h_counters[COUNTER_DENSE]; J.trunc += S.h_counters[COUNTER_TRUNC];
-        end_turn(J);
+        if (n_reads == 0) {
+            if (!wait_turn(J, seq)) return;
+            account();
+            end_turn(J);
+        }
     }
 }
 
-int run_text(cuclark_db* db, const uint8_t* text, size_t n, const cuclark_text_opts* o, cuclark_sink_fn sink, void* user,
-             cuclark_text_arrays* arrays, cuclark_text_stats* out) {
-    if (!db || (!text && n)) { set_error("null argument"); return CUCLARK_ERR_ARG; }
-    if (!db->d_table) { set_error("no database loaded"); return CUCLARK_ERR_STATE; }
+int run_text(cuclark_db* const* dbs, int n_dbs, const uint8_t* text, size_t n, const cuclark_text_opts* o,
+             cuclark_sink_fn sink, void* user, char* out_buf, size_t out_cap, cuclark_text_arrays* arrays,
+             cuclark_text_stats* out) {
+    if (!dbs || n_dbs < 1 || (!text && n)) { set_error("null argument"); return CUCLARK_ERR_ARG; }
+    for (int i = 0; i < n_dbs; i++) {
+        if (!dbs[i]) { set_error("null argument"); return CUCLARK_ERR_ARG; }
+        if (!dbs[i]->d_table) { set_error("no database loaded"); return CUCLARK_ERR_STATE; }
+        if (dbs[i]->cfg.shard_count > 1) { set_error("the text pipeline needs the whole table on each device (read-partitioned mode)"); return CUCLARK_ERR_STATE; }
+        if (dbs[i]->cfg.k != dbs[0]->cfg.k || dbs[i]->cfg.n_targets != dbs[0]->cfg.n_targets || dbs[i]->row_pairs != dbs[0]->row_pairs) {
+            set_error("handles of a multi-device run must share k, n_targets and row_pairs");
+            return CUCLARK_ERR_ARG;
+        }
+    }
     if (out) memset(out, 0, sizeof *out);
     const auto t0 = std::chrono::steady_clock::now();
     if (n == 0 || (text[0] != '>' && text[0] != '@')) {
         set_error("Failed to recognize the format of the file.");            // src/CuCLARK_hh.hh:1535-1538
         return CUCLARK_ERR_FORMAT;
     }
-    CK(cudaSetDevice(db->cfg.device));
     size_t chunk = o && o->chunk_bytes ? o->chunk_bytes : (size_t)64 << 20;
     chunk = std::min<size_t>(std::max<size_t>(chunk, 4096), (size_t)1 << 30);
     chunk = (chunk + 255) & ~(size_t)255;
     int n_slots = o && o->n_slots > 0 ? o->n_slots : 4;
     n_slots = std::min(n_slots, 16);
     const bool extended = o && o->extended;
-    int rc = ensure_pipe(db, chunk, n_slots, extended || (arrays && arrays->rows), o ? o->target_names : nullptr);
-    if (rc) return rc;
+    for (int i = 0; i < n_dbs; i++) {
+        CK(cudaSetDevice(dbs[i]->cfg.device));
+        int rc = ensure_pipe(dbs[i], chunk, n_slots, extended || (arrays && arrays->rows), o ? o->target_names : nullptr);
+        if (rc) return rc;
+    }
     Job J;
-    J.db = db; J.tp = db->text_pipe; J.text = text; J.n = n;
+    J.text = text; J.n = n;
     J.fastq = text[0] == '@';
     J.paired = o && o->paired; J.extended = extended;
     J.sink = sink; J.user = user; J.arrays = arrays;
+    J.out_buf = out_buf; J.out_cap = out_cap;
     cudaPointerAttributes attr;
     J.src_pinned = cudaPointerGetAttributes(&attr, text) == cudaSuccess && attr.type == cudaMemoryTypeHost;
     cudaGetLastError();
-    if (sink && !arrays) {
+    J.out_pinned = out_buf && cudaPointerGetAttributes(&attr, out_buf) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if ((sink || out_buf) && !arrays) {
         // header line (src/CuCLARK_hh.hh:1957-1972)
+        const TextPipe* tp = dbs[0]->text_pipe;
         std::string h = "Object_ID";
-        if (extended) for (size_t t = 1; t < J.tp->host_names.size(); t++) { h += ","; h += J.tp->host_names[t]; }
+        if (extended) for (size_t t = 1; t < tp->host_names.size(); t++) { h += ","; h += tp->host_names[t]; }
         h += ",Length,Gamma,1st_assignment,score1,2nd_assignment,score2,confidence\n";
-        if (sink(user, h.data(), h.size()) != 0) { set_error("the CSV sink reported an error"); return CUCLARK_ERR_IO; }
-        J.csv_bytes += h.size();
+        if (out_buf) {
+            if (h.size() > out_cap) { set_error("the output buffer is too small for the CSV"); return CUCLARK_ERR_NOMEM; }
+            memcpy(out_buf, h.data(), h.size());
+        }
+        if (sink && sink(user, h.data(), h.size(), 0) != 0) { set_error("the CSV sink reported an error"); return CUCLARK_ERR_IO; }
+        J.out_off = h.size();
     }
+    // one host thread per slot; slots of all devices pull chunks from the same cursor
     const size_t n_chunks_est = (n + chunk - 1) / chunk;
-    const int n_threads = (int)std::min<size_t>(n_slots, std::max<size_t>(n_chunks_est, 1));
     std::vector<std::thread> threads;
-    for (int i = 1; i < n_threads; i++) threads.emplace_back([&J, i] { worker(J, J.tp->slots[i]); });
-    worker(J, J.tp->slots[0]);
+    size_t started = 0;
+    for (int s = 0; s < n_slots && started < std::max<size_t>(n_chunks_est, 1); s++)
+        for (int i = 0; i < n_dbs && started < std::max<size_t>(n_chunks_est, 1); i++, started++) {
+            cuclark_db* db = dbs[i];
+            TextSlot* slot = &db->text_pipe->slots[s];
+            threads.emplace_back([&J, db, slot] { worker(J, db, *slot); });
+        }
     for (auto& t : threads) t.join();
     if (J.failed) { set_error("%s", J.err.c_str()); return J.rc; }
-    db->last_lookups = J.lookups; db->last_dense = J.dense; db->last_trunc = J.trunc;
+    dbs[0]->last_lookups = J.lookups; dbs[0]->last_dense = J.dense; dbs[0]->last_trunc = J.trunc;
     if (out) {
-        out->n_reads = J.n_reads; out->lookups = J.lookups; out->csv_bytes = J.csv_bytes; out->n_chunks = J.n_chunks;
+        out->n_reads = J.n_reads; out->lookups = J.lookups; out->csv_bytes = J.out_off; out->n_chunks = J.n_chunks;
         out->n_containers = J.n_cont; out->dense_reads = J.dense; out->truncated_rows = J.trunc;
         out->text_bytes = n;
         out->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -416,8 +452,15 @@ int run_text(cuclark_db* db, const uint8_t* text, size_t n, const cuclark_text_o
     return CUCLARK_OK;
 }
 
-int file_sink(void* user, const char* data, size_t n) {
-    return fwrite(data, 1, n, (FILE*)user) == n ? 0 : -1;
+// called concurrently from the slot threads, each with its own byte range of the file
+int file_sink(void* user, const char* data, size_t n, uint64_t offset) {
+    const int fd = (int)(intptr_t)user;
+    while (n) {
+        const ssize_t w = pwrite(fd, data, n, (off_t)offset);
+        if (w <= 0) return -1;
+        data += w; n -= (size_t)w; offset += (uint64_t)w;
+    }
+    return 0;
 }
 
 }  // namespace
@@ -429,18 +472,35 @@ extern "C" {
 
 int cuclark_classify_text(cuclark_db* db, const uint8_t* text, size_t n, const cuclark_text_opts* opts,
                           cuclark_sink_fn sink, void* user, cuclark_text_stats* out) {
-    return run_text(db, text, n, opts, sink, user, nullptr, out);
+    return run_text(&db, 1, text, n, opts, sink, user, nullptr, 0, nullptr, out);
+}
+
+int cuclark_classify_text_buffer(cuclark_db* const* dbs, int n_dbs, const uint8_t* text, size_t n,
+                                 const cuclark_text_opts* opts, char* out, size_t out_cap, size_t* out_len,
+                                 cuclark_text_stats* stats) {
+    if (!out || !out_len) { set_error("null argument"); return CUCLARK_ERR_ARG; }
+    cuclark_text_stats st;
+    const int rc = run_text(dbs, n_dbs, text, n, opts, nullptr, nullptr, out, out_cap, nullptr, &st);
+    *out_len = rc == CUCLARK_OK ? (size_t)st.csv_bytes : 0;
+    if (stats) *stats = st;
+    return rc;
+}
+
+int cuclark_classify_text_multi(cuclark_db* const* dbs, int n_dbs, const uint8_t* text, size_t n,
+                                const cuclark_text_opts* opts, cuclark_sink_fn sink, void* user,
+                                cuclark_text_stats* out) {
+    return run_text(dbs, n_dbs, text, n, opts, sink, user, nullptr, 0, nullptr, out);
 }
 
 int cuclark_text_debug(cuclark_db* db, const uint8_t* text, size_t n, const cuclark_text_opts* opts,
                        cuclark_text_arrays* arrays, cuclark_text_stats* out) {
     if (!arrays) { set_error("null argument"); return CUCLARK_ERR_ARG; }
-    return run_text(db, text, n, opts, nullptr, nullptr, arrays, out);
+    return run_text(&db, 1, text, n, opts, nullptr, nullptr, nullptr, 0, arrays, out);
 }
 
-int cuclark_classify_file(cuclark_db* db, const char* objects_path, const char* csv_path, const cuclark_text_opts* opts,
-                          cuclark_text_stats* out) {
-    if (!db || !objects_path || !csv_path) { set_error("null argument"); return CUCLARK_ERR_ARG; }
+int cuclark_classify_file_multi(cuclark_db* const* dbs, int n_dbs, const char* objects_path, const char* csv_path,
+                                const cuclark_text_opts* opts, cuclark_text_stats* out) {
+    if (!dbs || n_dbs < 1 || !objects_path || !csv_path) { set_error("null argument"); return CUCLARK_ERR_ARG; }
     const int fd = open(objects_path, O_RDONLY);
     struct stat sb;
     if (fd < 0 || fstat(fd, &sb) != 0 || sb.st_size == 0) {
@@ -452,15 +512,18 @@ int cuclark_classify_file(cuclark_db* db, const char* objects_path, const char* 
     void* map = mmap(nullptr, n, PROT_READ, MAP_PRIVATE, fd, 0);
     if (map == MAP_FAILED) { close(fd); set_error("Failed to mmapping the file."); return CUCLARK_ERR_IO; }
     madvise(map, n, MADV_SEQUENTIAL);
-    FILE* f = fopen(csv_path, "w");
-    if (!f) { munmap(map, n); close(fd); set_error("Failed to create/open file result: %s", csv_path); return CUCLARK_ERR_IO; }
-    std::vector<char> iobuf(8 << 20);
-    setvbuf(f, iobuf.data(), _IOFBF, iobuf.size());
-    int rc = run_text(db, (const uint8_t*)map, n, opts, file_sink, f, nullptr, out);
-    if (fclose(f) != 0 && rc == CUCLARK_OK) { set_error("failed to write %s", csv_path); rc = CUCLARK_ERR_IO; }
+    const int ofd = open(csv_path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    if (ofd < 0) { munmap(map, n); close(fd); set_error("Failed to create/open file result: %s", csv_path); return CUCLARK_ERR_IO; }
+    int rc = run_text(dbs, n_dbs, (const uint8_t*)map, n, opts, file_sink, (void*)(intptr_t)ofd, nullptr, 0, nullptr, out);
+    if (close(ofd) != 0 && rc == CUCLARK_OK) { set_error("failed to write %s", csv_path); rc = CUCLARK_ERR_IO; }
     munmap(map, n);
     close(fd);
     return rc;
+}
+
+int cuclark_classify_file(cuclark_db* db, const char* objects_path, const char* csv_path, const cuclark_text_opts* opts,
+                          cuclark_text_stats* out) {
+    return cuclark_classify_file_multi(&db, 1, objects_path, csv_path, opts, out);
 }
 
 }  // extern "C"

@@ -165,16 +165,33 @@ typedef struct cuclark_text_stats {
     double seconds;                    /* wall time of the call                                      */
 } cuclark_text_stats;
 
-/* returns 0 to continue, non-zero to abort (-> CUCLARK_ERR_IO) */
-typedef int (*cuclark_sink_fn)(void* user, const char* data, size_t n);
+/* Receives the CSV text piece by piece: `data[0..n)` belongs at byte `offset` of the result. Pieces
+ * may arrive from several threads at once and out of order (their ranges are disjoint and together
+ * cover the file); the header line comes first. Return 0 to continue, non-zero to abort
+ * (-> CUCLARK_ERR_IO). */
+typedef int (*cuclark_sink_fn)(void* user, const char* data, size_t n, uint64_t offset);
 
 /* `text` is host memory (pinned memory is copied from directly, pageable memory is staged). */
 int cuclark_classify_text(cuclark_db* db, const uint8_t* text, size_t n, const cuclark_text_opts* opts,
                           cuclark_sink_fn sink, void* user, cuclark_text_stats* out);
+/* Same, into a caller-provided host buffer; a pinned buffer receives the device's text directly. */
+int cuclark_classify_text_buffer(cuclark_db* const* dbs, int n_dbs, const uint8_t* text, size_t n,
+                                 const cuclark_text_opts* opts, char* out, size_t out_cap, size_t* out_len,
+                                 cuclark_text_stats* stats);
 /* CuCLARK::runSimple (src/CuCLARK_hh.hh:512-573): mmap `objects_path`, write `csv_path`.
  * CUCLARK_ERR_IO if the input is missing or empty ("Failed to open"). */
 int cuclark_classify_file(cuclark_db* db, const char* objects_path, const char* csv_path,
                           const cuclark_text_opts* opts, cuclark_text_stats* out);
+
+/* Read-partitioned multi-GPU in one process (the CLI's -d N): one handle per device, each holding
+ * the WHOLE table; chunks of the input are handed to whichever device has a free slot, the CSV
+ * stays in file order. (The reference's -d N partitions the table instead, src/CuClarkDB.cu:546-574;
+ * that mode is cfg.shard_count + cuclark_merge_rows_device.) */
+int cuclark_classify_text_multi(cuclark_db* const* dbs, int n_dbs, const uint8_t* text, size_t n,
+                                const cuclark_text_opts* opts, cuclark_sink_fn sink, void* user,
+                                cuclark_text_stats* out);
+int cuclark_classify_file_multi(cuclark_db* const* dbs, int n_dbs, const char* objects_path, const char* csv_path,
+                                const cuclark_text_opts* opts, cuclark_text_stats* out);
 
 /* Same pipeline, but instead of CSV text the intermediate arrays come back (host pointers, each
  * may be NULL): the read index (absolute byte offsets into `text`), the packed reads in the
@@ -198,6 +215,12 @@ int cuclark_synth_reads_device(cuclark_db* db, uint32_t seed, uint32_t genome_se
                                uint64_t genome_len, uint64_t first_read, size_t n_reads, int read_len,
                                int pct_random, int sub_per_10k, uint32_t* d_reads_ptr,
                                uint16_t* d_containers, void* stream);
+
+/* The same reads as 4-line FASTQ text, fixed-width records of 16 + 2*read_len bytes:
+ * "@r<9 digits>\n<bases>\n+\n<'I' x read_len>\n". d_text holds n_reads records. */
+int cuclark_synth_fastq_device(cuclark_db* db, uint32_t seed, uint32_t genome_seed, uint32_t n_targets,
+                               uint64_t genome_len, uint64_t first_read, size_t n_reads, int read_len,
+                               int pct_random, int sub_per_10k, uint8_t* d_text, void* stream);
 
 /* ---- roofline probe: random 32-byte-sector gather over this table ---------- */
 /* Reads n_probes uniformly random sectors of the loaded table per launch
