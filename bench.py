@@ -217,6 +217,9 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the host baseline)")
     torch.cuda.set_device(local)
     if world > 1:
+        # NCCL prints its version banner on stdout at some debug levels; stdout carries the JSON line only
+        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+            os.environ.pop("NCCL_DEBUG", None)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
