@@ -35,6 +35,7 @@ ABI_SYMBOLS = [
     "cuclark_synth_reads_device", "cuclark_synth_fastq_device", "cuclark_gather_bench",
     "cuclark_classify_text", "cuclark_classify_file", "cuclark_text_debug",
     "cuclark_classify_text_multi", "cuclark_classify_file_multi", "cuclark_classify_text_buffer",
+    "cuclark_build_database",
 ]
 
 
@@ -81,6 +82,16 @@ class TextArrays(C.Structure):
                 ("final5", C.c_void_p), ("rows", C.c_void_p)]
 
 
+class BuildOpts(C.Structure):
+    _fields_ = [("k", C.c_int), ("htsize", C.c_uint64), ("key_bytes", C.c_int), ("light_gap", C.c_int),
+                ("min_count", C.c_uint32), ("device", C.c_int)]
+
+
+class BuildStats(C.Structure):
+    _fields_ = [("n_nucleotides", C.c_uint64), ("n_kmers_added", C.c_uint64), ("n_kmers_kept", C.c_uint64),
+                ("key_bytes", C.c_int)]
+
+
 SINK_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64)
 
 _lib = None
@@ -124,6 +135,7 @@ def load_library():
     lib.cuclark_text_debug.argtypes = [vp, vp, sz, P(TextOpts), P(TextArrays), P(TextStats)]
     lib.cuclark_classify_text_multi.argtypes = [P(vp), ci, vp, sz, P(TextOpts), SINK_FN, vp, P(TextStats)]
     lib.cuclark_classify_text_buffer.argtypes = [P(vp), ci, vp, sz, P(TextOpts), vp, sz, P(sz), P(TextStats)]
+    lib.cuclark_build_database.argtypes = [P(BuildOpts), P(C.c_char_p), P(u16), sz, C.c_char_p, P(BuildStats)]
     lib.cuclark_classify_file_multi.argtypes = [P(vp), ci, C.c_char_p, C.c_char_p, P(TextOpts), P(TextStats)]
     for name in ABI_SYMBOLS:
         fn = getattr(lib, name)
@@ -145,6 +157,22 @@ def _np_from(ptr, n, dtype):
         return np.zeros(0, dtype)
     ct = {np.uint32: C.c_uint32, np.uint16: C.c_uint16}[dtype]
     return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ct)), shape=(n,))
+
+
+def build_database(target_files, target_labels, out_base: str, k: int, light: bool = False, light_gap: int = 0,
+                   min_count: int = 0, device: int = 0, htsize: int | None = None) -> dict:
+    """makeSpecificTargetSets + RemoveCommon + write on the device: FASTA targets -> <out_base>.sz/.ky/.lb.
+    `target_labels[i]` = label index of file i (order of first appearance in the targets file)."""
+    lib = load_library()
+    hts = htsize if htsize is not None else (HTSIZE_LIGHT if light else HTSIZE_FULL)
+    o = BuildOpts(k, hts, 0, (light_gap or 4) if light else 0, min_count, device)
+    files = (C.c_char_p * len(target_files))(*[f.encode() for f in target_files])
+    labels = (C.c_uint16 * len(target_labels))(*target_labels)
+    st = BuildStats()
+    rc = lib.cuclark_build_database(C.byref(o), files, labels, len(target_files), out_base.encode(), C.byref(st))
+    if rc != 0:
+        raise CuclarkError(rc, lib.cuclark_last_error().decode())
+    return {f: getattr(st, f) for f, _ in st._fields_}
 
 
 class CuClarkDB:

@@ -18,7 +18,7 @@ LIB = os.path.join(LIBDIR, "libcuclark_b200.so")
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-CU_SOURCES = ["table.cu", "classify.cu", "capi.cu", "textpipe.cu", "stream.cu"]
+CU_SOURCES = ["table.cu", "classify.cu", "capi.cu", "textpipe.cu", "stream.cu", "dbbuild.cu"]
 HEADERS = ["common.cuh", "internal.h", "synth.cuh", "textpipe.cuh", "fmt_g.h", os.path.join("..", "..", "include", "cuclark_b200.h")]
 
 

@@ -12,8 +12,8 @@
 // Differences, all in the direction of "less work for the caller":
 //  * -n / -b are accepted and echoed but only size the pipeline (chunks in flight);
 //  * -d N uses N GPUs read-partitioned (table replicated) instead of table-partitioned;
-//  * the database must already exist as <D>/db_central_*.{sz,ky,lb} (build it with the reference
-//    tools); building it on the host is not part of this library.
+//  * a missing database is built on the GPU (cuclark_build_database) from FASTA targets, byte-identical
+//    to the reference's files; --tsk, spectrum/FASTQ targets and the 3rd targets column are not supported.
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -101,6 +101,8 @@ struct Cli {
     string targets, folder, results;
     const char *objects = nullptr, *objects2 = nullptr;
     vector<string> labels, labels_c, names;     // names[0] = "NA"
+    vector<string> target_files;                // one per line of the targets file
+    vector<uint16_t> target_label;              // its label index
     vector<cuclark_db*> dbs;
     size_t n_objects = 0;
 };
@@ -132,6 +134,8 @@ static void read_targets(Cli& c) {
         }
         if (e.size() < 2) { cerr << " Missing label for " << e[0] << endl; exit(-1); }
         if (std::find(c.labels.begin(), c.labels.end(), e[1]) == c.labels.end()) c.labels.push_back(e[1]);
+        c.target_files.push_back(e[0]);
+        c.target_label.push_back((uint16_t)(std::find(c.labels.begin(), c.labels.end(), e[1]) - c.labels.begin()));
         if (e.size() > 2 && std::find(c.labels_c.begin(), c.labels_c.end(), e[2]) == c.labels_c.end())
             c.labels_c.push_back(e[2]);
     }
@@ -156,16 +160,36 @@ static void banner(const Cli& c) {
     exit(1);
 }
 
+// makeSpecificTargetSets (src/CuCLARK_hh.hh:691-1112) on the device: runs when the database files are absent
+static void build_database(Cli& c, const string& base) {
+    cerr << "Starting the creation of the database of targets specific " << c.k << "-mers from input files..." << endl;
+    if (!c.labels_c.empty()) {
+        cerr << "A third column (centromere labels) in the targets file is not supported by the device builder." << endl;
+        exit(-1);
+    }
+    cuclark_build_opts o;
+    memset(&o, 0, sizeof o);
+    o.k = (int)c.k;
+    o.htsize = HTSIZE;
+    o.light_gap = c.light ? (int)c.iter_kmers : 0;
+    o.min_count = c.min_t;
+    vector<const char*> files;
+    for (auto& f : c.target_files) files.push_back(f.c_str());
+    cuclark_build_stats st;
+    const int rc = cuclark_build_database(&o, files.data(), c.target_label.data(), files.size(), base.c_str(), &st);
+    if (rc == CUCLARK_ERR_NO_DEVICE) { cerr << "Not enough CUDA devices found: " << cuclark_last_error() << endl; exit(1); }
+    if (rc) die_lib("cuclark_build_database");
+    cerr << st.n_nucleotides << " nt read in total." << endl;
+    cerr << "Removal of common k-mers done: " << st.n_kmers_kept << " specific " << c.k << "-mers found." << endl;
+    cerr << (c.light ? "Creating light database in disk..." : "Creating database in disk...") << endl;
+    cerr << st.n_kmers_kept << " " << c.k << "-mers successfully stored in database." << endl;
+}
+
 static void load_database(Cli& c) {
     const string base = db_name(c);
-    for (const char* ext : {".sz", ".ky", ".lb"}) {
-        if (!valid_file((base + ext).c_str())) {
-            cerr << "Failed to find the database." << endl;
-            cerr << "[" << base << ".*] is missing: this build classifies against an existing database; "
-                 << "create it once with the reference cuCLARK" << (c.light ? "-l" : "") << " (same -T/-D/-k)." << endl;
-            exit(-1);
-        }
-    }
+    bool present = true;
+    for (const char* ext : {".sz", ".ky", ".lb"}) present = present && valid_file((base + ext).c_str());
+    if (!present) build_database(c, base);
     int n_dev = (int)c.devices;
     if (n_dev == 0) n_dev = 1;
     cerr << "Loading database [" << base << ".*] (s=" << c.sfactor << ")..." << endl;

@@ -139,6 +139,32 @@ int cuclark_classify_device(cuclark_db* db, const uint32_t* d_reads_ptr, const u
 int cuclark_merge_rows_device(cuclark_db* db, const uint16_t* d_rows_parts, int n_parts, size_t n_reads,
                               uint16_t* d_rows_out, uint16_t* d_final5, void* stream);
 
+/* ---- database construction on the device -------------------------------------------------------
+ * makeSpecificTargetSets + EHashtable::addElement + RemoveCommon + hTable::write
+ * (src/CuCLARK_hh.hh:691-1112, src/HashTableStorage_hh.hh:242-292 and 484-523,
+ * src/hashTable_hh.hh:591-663): scans the FASTA target files, takes every overlapping k-mer
+ * (light_gap = 0, cuCLARK) or every light_gap-th non-overlapping one (cuCLARK-l), keeps the
+ * canonical k-mers that occur under exactly one label more than min_count times and writes
+ * <out_base>.sz/.ky/.lb byte for byte as the reference does. target_labels[i] is the label index
+ * of file i (labels numbered in order of first appearance in the targets file). */
+typedef struct cuclark_build_opts {
+    int k;
+    uint64_t htsize;      /* CUCLARK_HTSIZE_FULL or CUCLARK_HTSIZE_LIGHT                               */
+    int key_bytes;        /* 0 = as src/main.cc:278-316                                               */
+    int light_gap;        /* 0 = full variant; >= 1: -g of cuCLARK-l (default there: 4)               */
+    uint32_t min_count;   /* -t                                                                       */
+    int device;
+} cuclark_build_opts;
+typedef struct cuclark_build_stats {
+    uint64_t n_nucleotides;   /* ACGTU bytes outside header lines                                     */
+    uint64_t n_kmers_added;   /* addElement calls                                                     */
+    uint64_t n_kmers_kept;    /* entries written                                                      */
+    int key_bytes;
+} cuclark_build_stats;
+int cuclark_build_database(const cuclark_build_opts* opts, const char* const* target_files,
+                           const uint16_t* target_labels, size_t n_files, const char* out_base,
+                           cuclark_build_stats* stats);
+
 /* ---- text in, CSV out: CuCLARK::getObjectsDataComputeFullGPU + printExtendedResultsSynced --------
  * (src/CuCLARK_hh.hh:1335-1790 and 1951-2139). The reference indexes reads (:1340-1534) and packs
  * them (:1616-1708) on the host and prints one CSV line per read with fprintf (:2097-2136). Here

@@ -9,6 +9,8 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 GOLDEN = os.path.join(ROOT, "tests", "golden")
+sys.path.insert(0, GOLDEN)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
 def pytest_configure(config):
