@@ -35,7 +35,7 @@ ABI_SYMBOLS = [
     "cuclark_synth_reads_device", "cuclark_synth_fastq_device", "cuclark_gather_bench",
     "cuclark_classify_text", "cuclark_classify_file", "cuclark_text_debug",
     "cuclark_classify_text_multi", "cuclark_classify_file_multi", "cuclark_classify_text_buffer",
-    "cuclark_build_database",
+    "cuclark_build_database", "cuclark_save_table", "cuclark_load_table",
 ]
 
 
@@ -136,6 +136,8 @@ def load_library():
     lib.cuclark_classify_text_multi.argtypes = [P(vp), ci, vp, sz, P(TextOpts), SINK_FN, vp, P(TextStats)]
     lib.cuclark_classify_text_buffer.argtypes = [P(vp), ci, vp, sz, P(TextOpts), vp, sz, P(sz), P(TextStats)]
     lib.cuclark_build_database.argtypes = [P(BuildOpts), P(C.c_char_p), P(u16), sz, C.c_char_p, P(BuildStats)]
+    lib.cuclark_save_table.argtypes = [vp, C.c_char_p]
+    lib.cuclark_load_table.argtypes = [vp, C.c_char_p, C.c_char_p, ci]
     lib.cuclark_classify_file_multi.argtypes = [P(vp), ci, C.c_char_p, C.c_char_p, P(TextOpts), P(TextStats)]
     for name in ABI_SYMBOLS:
         fn = getattr(lib, name)
@@ -241,6 +243,20 @@ class CuClarkDB:
         assert sz.size == self.htsize
         self._check(self._lib.cuclark_load_db_arrays(self._h, sz.ctypes.data, ky.ctypes.data, lb.ctypes.data,
                                                       ky.size, mod_collision))
+
+    def save_table(self, path: str):
+        """Write the loaded table in its device layout (cuclark_save_table)."""
+        self._check(self._lib.cuclark_save_table(self._h, path.encode()))
+
+    def load_table(self, path: str, src_base: str | None = None, mod_collision: int = 1) -> bool:
+        """Stream a table cache back into HBM. False if the file is missing, is no cache, is corrupt
+        or belongs to another configuration / other source files (the caller then calls read())."""
+        rc = self._lib.cuclark_load_table(self._h, path.encode(), src_base.encode() if src_base else None,
+                                          mod_collision)
+        if rc in (-4, -8):      # CUCLARK_ERR_IO, CUCLARK_ERR_FORMAT
+            return False
+        self._check(rc)
+        return True
 
     def build_synthetic(self, seed: int, n_targets: int, genome_len: int, light_gap: int = 0):
         self._check(self._lib.cuclark_build_db_synthetic(self._h, seed, n_targets, genome_len, light_gap))

@@ -176,6 +176,21 @@ int cuclark_load_db_arrays(cuclark_db* db, const uint8_t* sz, const void* ky, co
     return table_build_from_arrays(db, sz, ky, lb, n_entries, sfactor, nullptr);
 }
 
+int cuclark_save_table(cuclark_db* db, const char* path) {
+    if (!db || !path) { set_error("null argument"); return CUCLARK_ERR_ARG; }
+    int rc = use_device(db);
+    if (rc) return rc;
+    return table_save(db, path);
+}
+
+int cuclark_load_table(cuclark_db* db, const char* path, const char* src_base, int sfactor) {
+    if (!db || !path) { set_error("null argument"); return CUCLARK_ERR_ARG; }
+    int rc = use_device(db);
+    if (rc) return rc;
+    table_free(db);
+    return table_load(db, path, src_base, sfactor);
+}
+
 int cuclark_build_db_synthetic(cuclark_db* db, uint32_t seed, uint32_t n_targets, uint64_t genome_len, int light_gap) {
     if (!db) { set_error("null argument"); return CUCLARK_ERR_ARG; }
     if ((int)n_targets > db->cfg.n_targets) { set_error("n_targets exceeds the handle's n_targets"); return CUCLARK_ERR_ARG; }

@@ -59,6 +59,7 @@ static void print_usage() {
          << "-s <factor>           sampling factor when loading the database (cuCLARK only)\n"
          << "--tsk                 accepted for compatibility\n"
          << "--extended            one hit-count column per target in the results\n"
+         << "--cache               keep the device-layout table next to the database (<db>.b200) and reuse it\n"
          << "--help, --version\n"
          << endl;
 }
@@ -97,7 +98,7 @@ static bool get_line(FILE* f, string& line) {
 struct Cli {
     size_t k = 31, cpu = 1, iter_kmers = 0, batches = 1, devices = 0;
     unsigned min_t = 0, sfactor = 1;
-    bool light = false, tsk = false, ext = false;
+    bool light = false, tsk = false, ext = false, cache = false;
     string targets, folder, results;
     const char *objects = nullptr, *objects2 = nullptr;
     vector<string> labels, labels_c, names;     // names[0] = "NA"
@@ -208,9 +209,25 @@ static void load_database(Cli& c) {
             exit(1);
         }
         if (rc) die_lib("cuclark_create");
-        rc = cuclark_load_db_files(db, base.c_str(), (int)c.sfactor);
-        if (rc == CUCLARK_ERR_IO) { cerr << cuclark_last_error() << endl << "Failed to find the database." << endl; exit(-1); }
-        if (rc) die_lib("cuclark_load_db_files");
+        // --cache: <base>[.s<f>].b200 holds the table in its device layout; written after the first
+        // load from .sz/.ky/.lb, streamed back (no rebuild) while it still matches those files
+        const string cache = base + (c.sfactor > 1 ? ".s" + std::to_string(c.sfactor) : string()) + ".b200";
+        bool from_cache = false;
+        if (c.cache && valid_file(cache.c_str())) {
+            rc = cuclark_load_table(db, cache.c_str(), base.c_str(), (int)c.sfactor);
+            if (rc == CUCLARK_OK) { from_cache = true; if (d == 0) cerr << "Table cache " << cache << " loaded." << endl; }
+            else if (rc == CUCLARK_ERR_FORMAT || rc == CUCLARK_ERR_IO) cerr << "Ignoring table cache: " << cuclark_last_error() << endl;
+            else die_lib("cuclark_load_table");
+        }
+        if (!from_cache) {
+            rc = cuclark_load_db_files(db, base.c_str(), (int)c.sfactor);
+            if (rc == CUCLARK_ERR_IO) { cerr << cuclark_last_error() << endl << "Failed to find the database." << endl; exit(-1); }
+            if (rc) die_lib("cuclark_load_db_files");
+            if (c.cache && d == 0) {
+                if (cuclark_save_table(db, cache.c_str()) == CUCLARK_OK) cerr << "Table cache " << cache << " written." << endl;
+                else cerr << "Table cache not written: " << cuclark_last_error() << endl;
+            }
+        }
         c.dbs.push_back(db);
     }
 }
@@ -370,6 +387,8 @@ int main(int argc, char** argv) {
             if (c.cpu < 1) { cerr << "The number of threads should be higher than 0." << endl; exit(1); }
         } else if (v == "--tsk") {
             c.tsk = true;
+        } else if (v == "--cache") {
+            c.cache = true;
         } else if (v == "--extended") {
             c.ext = true;
         } else if (v == "-T") {

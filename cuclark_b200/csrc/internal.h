@@ -53,6 +53,8 @@ struct cuclark_db {
     uint4* d_ovf = nullptr;            // overflow table
     cuclark::TableView view{};
     uint64_t n_entries = 0, n_spilled = 0, n_spill_buckets = 0;
+    int src_sfactor = 1;               // -s the table was built with, and the sizes of its source files
+    uint64_t src_bytes[3] = {0, 0, 0}; //   (.sz/.ky/.lb; 0 when built from arrays or synthetic): table cache header
     // classify scratch (one-shot calls; batches carry their own)
     cuclark::Scratch scratch;
     uint32_t* d_dense_hist = nullptr;  // dense_blocks * n_targets, shared: dense kernels are
@@ -81,6 +83,8 @@ int table_build_from_arrays(cuclark_db* db, const uint8_t* sz, const void* ky, c
                             uint64_t n_entries_file, int sfactor, const char* base_path);
 int table_build_synthetic(cuclark_db* db, uint32_t seed, uint32_t n_targets, uint64_t genome_len, int light_gap);
 void table_free(cuclark_db* db);
+int table_save(cuclark_db* db, const char* path);
+int table_load(cuclark_db* db, const char* path, const char* src_base, int sfactor);
 
 // classify.cu
 int classify_launch(cuclark_db* db, const Scratch& sc, const uint32_t* d_ptr, const uint16_t* d_cont, size_t n_reads,

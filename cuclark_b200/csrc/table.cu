@@ -498,6 +498,8 @@ void table_free(cuclark_db* db) {
     db->d_ovf = nullptr;
     db->view = TableView{};
     db->n_entries = db->n_spilled = db->n_spill_buckets = 0;
+    db->src_sfactor = 1;
+    db->src_bytes[0] = db->src_bytes[1] = db->src_bytes[2] = 0;
 }
 
 int table_build_from_arrays(cuclark_db* db, const uint8_t* sz_in, const void* ky, const uint16_t* lb,
@@ -541,6 +543,10 @@ int table_build_from_arrays(cuclark_db* db, const uint8_t* sz_in, const void* ky
         } else kept += s;
     }
     coarse[n_blocks] = total;
+    db->src_sfactor = sfactor > 1 ? sfactor : 1;
+    db->src_bytes[0] = base_path ? H : 0;
+    db->src_bytes[1] = base_path ? total * (uint64_t)kb : 0;
+    db->src_bytes[2] = base_path ? total * 2 : 0;
     if (!base_path && total != n_entries_file) { set_error("bucket sizes sum to %llu entries but %llu were passed", (unsigned long long)total, (unsigned long long)n_entries_file); return CUCLARK_ERR_ARG; }
 
     // largest chunk, for the staging buffers
@@ -656,6 +662,197 @@ int table_build_synthetic(cuclark_db* db, uint32_t seed, uint32_t n_targets, uin
         if (rc != CUCLARK_OK) bb.free_all();
     }
     return rc;
+}
+
+// ---- table cache: the device layout as one file --------------------------------------------------
+// SURVEY.md section 8(f)-3. The reference loader reads .sz/.ky/.lb serially into pinned memory and
+// rebuilds its bucket pointers on every start (src/CuClarkDB.cu:462-808); here the re-bucketed table
+// can be written once and streamed back: file -> pinned double buffer -> H2D, no rebuild.
+namespace {
+
+constexpr char CACHE_MAGIC[8] = {'C', 'U', 'C', 'B', '2', 'T', 'B', 'L'};
+constexpr uint32_t CACHE_VERSION = 1;
+constexpr size_t CACHE_IO_BYTES = 64ull << 20;
+
+struct CacheHeader {                 // 192 bytes, little endian
+    char magic[8];
+    uint32_t version, header_bytes;
+    uint32_t k, layout, n_targets, key_bytes, shard_index, shard_count, sfactor, reserved;
+    uint64_t htsize, M, lo, n_local, n_ovf, n_entries, n_spilled, n_spill_buckets;
+    uint64_t src_bytes[3];           // sizes of the .sz/.ky/.lb the table was built from (0: not from files)
+    uint64_t checksum;               // wrapping sum of the payload's 64-bit words times their position parity
+    uint64_t pad[6];
+};
+static_assert(sizeof(CacheHeader) == 192, "cache header layout");
+
+// order-sensitive checksum of a device buffer of 64-bit words: sum of w[i] * (2*(i mod 2^20) + 1)
+__global__ void k_checksum(const uint64_t* __restrict__ w, uint64_t n, unsigned long long* out) {
+    uint64_t acc = 0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += gridDim.x * (uint64_t)blockDim.x)
+        acc += w[i] * (2 * (i & 0xFFFFFu) + 1);
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, (unsigned long long)acc);
+}
+
+int device_checksum(cuclark_db* db, const uint4* table, uint64_t n_table, const uint4* ovf, uint64_t n_ovf, uint64_t* out) {
+    unsigned long long* d = nullptr;
+    CK(cudaMalloc(&d, 16));
+    CK(cudaMemset(d, 0, 16));
+    const int blocks = db->sm_count * 8;
+    if (n_table) k_checksum<<<blocks, 256>>>(reinterpret_cast<const uint64_t*>(table), n_table * 4, d);
+    if (n_ovf) k_checksum<<<blocks, 256>>>(reinterpret_cast<const uint64_t*>(ovf), n_ovf * 4, d + 1);
+    unsigned long long h[2];
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) { set_error("checksum kernel failed: %s", cudaGetErrorString(e)); return CUCLARK_ERR_CUDA; }
+    *out = h[0] ^ (h[1] * 0x9E3779B97F4A7C15ull);
+    return CUCLARK_OK;
+}
+
+struct IoBuffers {
+    void* h[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    cudaStream_t st = nullptr;
+    int init() {
+        for (int i = 0; i < 2; i++) {
+            CK(cudaMallocHost(&h[i], CACHE_IO_BYTES));
+            CK(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+        }
+        CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        return CUCLARK_OK;
+    }
+    ~IoBuffers() {
+        for (int i = 0; i < 2; i++) { if (h[i]) cudaFreeHost(h[i]); if (ev[i]) cudaEventDestroy(ev[i]); }
+        if (st) cudaStreamDestroy(st);
+    }
+};
+
+// device -> file, the copy of piece i+1 overlapping the write of piece i
+int stream_out(IoBuffers& io, FILE* f, const void* d_src, uint64_t bytes, const char* path) {
+    const uint8_t* src = static_cast<const uint8_t*>(d_src);
+    const uint64_t n_pieces = (bytes + CACHE_IO_BYTES - 1) / CACHE_IO_BYTES;
+    auto piece = [&](uint64_t i) { return std::min<uint64_t>(CACHE_IO_BYTES, bytes - i * CACHE_IO_BYTES); };
+    if (n_pieces) { CK(cudaMemcpyAsync(io.h[0], src, piece(0), cudaMemcpyDeviceToHost, io.st)); CK(cudaEventRecord(io.ev[0], io.st)); }
+    for (uint64_t i = 0; i < n_pieces; i++) {
+        if (i + 1 < n_pieces) {
+            CK(cudaMemcpyAsync(io.h[(i + 1) & 1], src + (i + 1) * CACHE_IO_BYTES, piece(i + 1), cudaMemcpyDeviceToHost, io.st));
+            CK(cudaEventRecord(io.ev[(i + 1) & 1], io.st));
+        }
+        CK(cudaEventSynchronize(io.ev[i & 1]));
+        if (fwrite(io.h[i & 1], 1, piece(i), f) != piece(i)) { set_error("write to %s failed", path); return CUCLARK_ERR_IO; }
+    }
+    return CUCLARK_OK;
+}
+
+// file -> device, the read of piece i+1 overlapping the copy of piece i
+int stream_in(IoBuffers& io, FILE* f, void* d_dst, uint64_t bytes, const char* path) {
+    uint8_t* dst = static_cast<uint8_t*>(d_dst);
+    const uint64_t n_pieces = (bytes + CACHE_IO_BYTES - 1) / CACHE_IO_BYTES;
+    for (uint64_t i = 0; i < n_pieces; i++) {
+        const uint64_t n = std::min<uint64_t>(CACHE_IO_BYTES, bytes - i * CACHE_IO_BYTES);
+        if (i >= 2) CK(cudaEventSynchronize(io.ev[i & 1]));      // the copy that last used this buffer
+        if (fread(io.h[i & 1], 1, n, f) != n) { set_error("%s is truncated", path); return CUCLARK_ERR_IO; }
+        CK(cudaMemcpyAsync(dst + i * CACHE_IO_BYTES, io.h[i & 1], n, cudaMemcpyHostToDevice, io.st));
+        CK(cudaEventRecord(io.ev[i & 1], io.st));
+    }
+    CK(cudaStreamSynchronize(io.st));
+    return CUCLARK_OK;
+}
+
+uint64_t file_size_or_zero(const std::string& p) {
+    FILE* f = fopen(p.c_str(), "rb");
+    if (!f) return 0;
+    fseeko(f, 0, SEEK_END);
+    const uint64_t n = (uint64_t)ftello(f);
+    fclose(f);
+    return n;
+}
+
+}  // namespace
+
+int table_save(cuclark_db* db, const char* path) {
+    if (!db->d_table) { set_error("no database loaded"); return CUCLARK_ERR_STATE; }
+    CacheHeader h;
+    memset(&h, 0, sizeof h);
+    memcpy(h.magic, CACHE_MAGIC, 8);
+    h.version = CACHE_VERSION; h.header_bytes = sizeof h;
+    h.k = db->cfg.k; h.layout = db->view.layout; h.n_targets = db->cfg.n_targets; h.key_bytes = db->key_bytes;
+    h.shard_index = db->cfg.shard_index; h.shard_count = db->cfg.shard_count; h.sfactor = db->src_sfactor;
+    h.htsize = db->cfg.htsize; h.M = db->view.M; h.lo = db->view.lo; h.n_local = db->view.n_local; h.n_ovf = db->view.n_ovf;
+    h.n_entries = db->n_entries; h.n_spilled = db->n_spilled; h.n_spill_buckets = db->n_spill_buckets;
+    for (int i = 0; i < 3; i++) h.src_bytes[i] = db->src_bytes[i];
+    CK(cudaDeviceSynchronize());
+    int rc = device_checksum(db, db->d_table, h.n_local, db->d_ovf, h.n_ovf, &h.checksum);
+    if (rc) return rc;
+    const std::string tmp = std::string(path) + ".tmp";
+    FILE* f = fopen(tmp.c_str(), "wb");
+    if (!f) { set_error("Failed to open %s for writing", tmp.c_str()); return CUCLARK_ERR_IO; }
+    IoBuffers io;
+    rc = io.init();
+    if (rc == CUCLARK_OK && fwrite(&h, sizeof h, 1, f) != 1) { set_error("write to %s failed", tmp.c_str()); rc = CUCLARK_ERR_IO; }
+    if (rc == CUCLARK_OK) rc = stream_out(io, f, db->d_table, h.n_local * 32, tmp.c_str());
+    if (rc == CUCLARK_OK && h.n_ovf) rc = stream_out(io, f, db->d_ovf, h.n_ovf * 32, tmp.c_str());
+    if (fclose(f) != 0 && rc == CUCLARK_OK) { set_error("write to %s failed", tmp.c_str()); rc = CUCLARK_ERR_IO; }
+    if (rc == CUCLARK_OK && rename(tmp.c_str(), path) != 0) { set_error("cannot rename %s to %s", tmp.c_str(), path); rc = CUCLARK_ERR_IO; }
+    if (rc != CUCLARK_OK) remove(tmp.c_str());
+    return rc;
+}
+
+int table_load(cuclark_db* db, const char* path, const char* src_base, int sfactor) {
+    FILE* f = fopen(path, "rb");
+    if (!f) { set_error("Failed to open %s", path); return CUCLARK_ERR_IO; }
+    struct Closer { FILE* f; ~Closer() { fclose(f); } } closer{f};
+    CacheHeader h;
+    if (fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, CACHE_MAGIC, 8) != 0 || h.header_bytes != sizeof h) {
+        set_error("%s is not a cuclark_b200 table cache", path); return CUCLARK_ERR_FORMAT;
+    }
+    if (h.version != CACHE_VERSION) { set_error("%s: cache version %u, this library reads %u", path, h.version, CACHE_VERSION); return CUCLARK_ERR_FORMAT; }
+    const int want_s = sfactor > 1 ? sfactor : 1;
+    if ((int)h.k != db->cfg.k || h.htsize != db->cfg.htsize || (int)h.n_targets != db->cfg.n_targets ||
+        (int)h.shard_index != db->cfg.shard_index || (int)h.shard_count != db->cfg.shard_count || (int)h.sfactor != want_s ||
+        (db->cfg.layout != 0 && (int)h.layout != db->cfg.layout)) {
+        set_error("%s was written for another configuration (k=%u htsize=%llu targets=%u shard %u/%u s=%u layout %u)", path, h.k,
+                  (unsigned long long)h.htsize, h.n_targets, h.shard_index, h.shard_count, h.sfactor, h.layout);
+        return CUCLARK_ERR_FORMAT;
+    }
+    if ((h.layout != LAYOUT_NARROW && h.layout != LAYOUT_WIDE) || h.M == 0 || h.n_local == 0 || h.n_local >= 0xFFFFFFFFull ||
+        h.lo + h.n_local > h.M || (h.layout == LAYOUT_NARROW && (h.k >= 32 || pow4((int)h.k) / h.M >= 0xFFFFFFFFull))) {
+        set_error("%s: inconsistent geometry", path); return CUCLARK_ERR_FORMAT;
+    }
+    if (src_base) {
+        const std::string b(src_base);
+        const char* ext[3] = {".sz", ".ky", ".lb"};
+        for (int i = 0; i < 3; i++) {
+            if (file_size_or_zero(b + ext[i]) != h.src_bytes[i]) {
+                set_error("%s does not belong to %s%s (size differs)", path, src_base, ext[i]); return CUCLARK_ERR_FORMAT;
+            }
+        }
+    }
+    fseeko(f, 0, SEEK_END);
+    if ((uint64_t)ftello(f) != sizeof h + (h.n_local + h.n_ovf) * 32) { set_error("%s is truncated", path); return CUCLARK_ERR_FORMAT; }
+    fseeko(f, sizeof h, SEEK_SET);
+    uint4 *table = nullptr, *ovf = nullptr;
+    if (cudaMalloc(&table, h.n_local * 32) != cudaSuccess) { cudaGetLastError(); set_error("cudaMalloc of %.2f GB table failed", h.n_local * 32 / 1e9); return CUCLARK_ERR_NOMEM; }
+    if (h.n_ovf && cudaMalloc(&ovf, h.n_ovf * 32) != cudaSuccess) { cudaGetLastError(); cudaFree(table); set_error("cudaMalloc of overflow table failed"); return CUCLARK_ERR_NOMEM; }
+    IoBuffers io;
+    int rc = io.init();
+    if (rc == CUCLARK_OK) rc = stream_in(io, f, table, h.n_local * 32, path);
+    if (rc == CUCLARK_OK && h.n_ovf) rc = stream_in(io, f, ovf, h.n_ovf * 32, path);
+    uint64_t sum = 0;
+    if (rc == CUCLARK_OK) rc = device_checksum(db, table, h.n_local, ovf, h.n_ovf, &sum);
+    if (rc == CUCLARK_OK && sum != h.checksum) { set_error("%s: checksum mismatch (file is corrupt)", path); rc = CUCLARK_ERR_FORMAT; }
+    if (rc != CUCLARK_OK) { cudaFree(table); cudaFree(ovf); return rc; }
+    db->d_table = table; db->d_ovf = ovf;
+    db->view = TableView{};
+    db->view.buckets = table; db->view.ovf = ovf;
+    db->view.M = h.M; db->view.magic = (uint64_t)((((__uint128_t)1) << 64) / h.M);
+    db->view.lo = h.lo; db->view.n_local = h.n_local; db->view.n_ovf = h.n_ovf;
+    db->view.layout = (int)h.layout; db->view.k = db->cfg.k;
+    db->n_entries = h.n_entries; db->n_spilled = h.n_spilled; db->n_spill_buckets = h.n_spill_buckets;
+    db->src_sfactor = (int)h.sfactor;
+    for (int i = 0; i < 3; i++) db->src_bytes[i] = h.src_bytes[i];
+    return CUCLARK_OK;
 }
 
 }  // namespace cuclark

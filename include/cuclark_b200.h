@@ -106,6 +106,18 @@ int cuclark_load_db_arrays(cuclark_db* db, const uint8_t* sz, const void* ky, co
 int cuclark_build_db_synthetic(cuclark_db* db, uint32_t seed, uint32_t n_targets, uint64_t genome_len,
                                int light_gap);
 
+/* ---- table cache -----------------------------------------------------------
+ * The reference re-reads .sz/.ky/.lb and rebuilds its bucket pointers on every start
+ * (CuClarkDB::read, src/CuClarkDB.cu:462-808). cuclark_save_table writes the loaded table in its
+ * DEVICE layout (192-byte header, sector buckets, overflow table; checksummed) so that a later
+ * cuclark_load_table streams it back file -> pinned buffer -> HBM without rebuilding.
+ * cuclark_load_table returns CUCLARK_ERR_IO if `path` cannot be opened and CUCLARK_ERR_FORMAT if
+ * the file is not a cache, is corrupt, was written for another k / HTSIZE / n_targets / shard /
+ * sampling factor, or (src_base != NULL) if <src_base>.sz/.ky/.lb are not the files it was
+ * built from (compared by size); the caller then falls back to cuclark_load_db_files. */
+int cuclark_save_table(cuclark_db* db, const char* path);
+int cuclark_load_table(cuclark_db* db, const char* path, const char* src_base, int sfactor);
+
 int cuclark_get_stats(cuclark_db* db, cuclark_stats* out);
 /* Fetch the counters (lookups, dense_reads, truncated_rows) of the last
  * cuclark_classify_device call; synchronises `stream` (NULL = library stream). */

@@ -183,3 +183,30 @@ def test_cli_full_fastq_equals_reference_csv(exes, full_small, tmp_path):
     assert p.returncode == 0, p.stderr
     ref = gzip.open(os.path.join(GOLDEN, "full_small.csv.gz")).read()
     assert (tmp_path / "out.csv").read_bytes() == ref
+
+
+@pytest.mark.gpu
+def test_cli_table_cache(exes, light_small, tmp_path):
+    """--cache: the first run writes <db>.b200, the second streams it back; a stale cache is ignored and
+    rewritten. The CSV is the reference binary's in all three runs."""
+    reads = setup_case(light_small, str(tmp_path))
+    ref = gzip.open(os.path.join(GOLDEN, "light_small.csv.gz")).read()
+    cmd = [exes[1], "-T", "targets.txt", "-D", "db/", "-O", os.path.basename(reads), "-R", "out", "--cache"]
+    cache = tmp_path / "db" / "db_central_k27_t8_s57777779_m0_light_4.tsk.b200"
+    p = run(cmd, cwd=str(tmp_path))
+    assert p.returncode == 0, p.stderr
+    assert "written." in p.stderr and cache.exists()
+    assert (tmp_path / "out.csv").read_bytes() == ref
+    os.remove(tmp_path / "out.csv")
+    p = run(cmd, cwd=str(tmp_path))
+    assert p.returncode == 0, p.stderr
+    assert "Table cache" in p.stderr and "loaded." in p.stderr and "written." not in p.stderr
+    assert (tmp_path / "out.csv").read_bytes() == ref
+    # damage the cache: it is refused, the database files are used, the cache is rewritten
+    blob = bytearray(cache.read_bytes()); blob[4096] ^= 1
+    cache.write_bytes(blob)
+    os.remove(tmp_path / "out.csv")
+    p = run(cmd, cwd=str(tmp_path))
+    assert p.returncode == 0, p.stderr
+    assert "Ignoring table cache" in p.stderr and "written." in p.stderr
+    assert (tmp_path / "out.csv").read_bytes() == ref
