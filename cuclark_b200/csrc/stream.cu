@@ -34,10 +34,13 @@ struct TextSlot {
     uint32_t* h_counters = nullptr;  // pinned
     Scratch scratch;
     cudaStream_t stream = nullptr;
+    void* d_arena = nullptr;         // every device array of the slot is carved from ONE allocation,
+    void* h_arena = nullptr;         //   every pinned one from another: a slot costs two driver calls
+    bool with_stage = false;         // h_text is present
 };
 
 struct TextPipe {
-    std::vector<TextSlot> slots;
+    std::vector<TextSlot> slots;     // allocated lazily, each by the thread that first uses it
     size_t chunk_bytes = 0;
     bool extended = false;
     int row_pairs = 0;
@@ -50,59 +53,73 @@ struct TextPipe {
 
 namespace {
 
-template <typename T>
-int dmalloc(T*& p, size_t count) {
-    CK(cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T)));
-    return CUCLARK_OK;
-}
-
 void free_slot(TextSlot& s) {
     if (s.stream) cudaStreamSynchronize(s.stream);
-    TextSlotDev& d = s.d;
-    cudaFree(d.text); cudaFree(d.line_start); cudaFree(d.hdr_line); cudaFree(d.name_s); cudaFree(d.name_e);
-    cudaFree(d.seq_s); cudaFree(d.seq_e); cudaFree(d.len); cudaFree(d.reads_ptr); cudaFree(d.cont);
-    cudaFree(d.final5); cudaFree(d.rows); cudaFree(d.csv_off); cudaFree(d.csv); cudaFree(d.tile_a); cudaFree(d.tile_b);
-    cudaFree(d.info);
-    cudaFreeHost(s.h_text); cudaFreeHost(s.h_csv); cudaFreeHost(s.h_info); cudaFreeHost(s.h_counters);
-    cudaFree(s.scratch.d_counters); cudaFree(s.scratch.d_dense_list);
+    cudaFree(s.d_arena);
+    cudaFreeHost(s.h_arena);
     if (s.stream) cudaStreamDestroy(s.stream);
     s = TextSlot{};
 }
 
-int alloc_slot(TextSlot& s, size_t C, bool extended, int row_pairs) {
+// bump allocator over one arena: first pass (base == nullptr) only sizes it
+struct Carver {
+    uint8_t* base;
+    size_t off = 0;
+    template <typename T>
+    void take(T*& p, size_t count) {
+        off = (off + 255) & ~(size_t)255;
+        p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+        off += count * sizeof(T);
+    }
+};
+
+// Pinned memory costs ~0.6 ms per MiB to allocate on the B200 host (16 slots of 64 MiB chunks took
+// 3.6 s, the classification of 2 M reads 40 ms), so a slot is sized tightly and allocated by its own
+// thread while the other slots already work. `with_stage`: the source is pageable and needs h_text.
+int alloc_slot(TextSlot& s, size_t C, bool extended, int row_pairs, bool with_stage) {
     TextSlotDev& d = s.d;
     d.cap_bytes = C;
     d.cap_lines = C / 6 + 64;
     d.cap_reads = C / 16 + 64;
     d.cap_cont = C / 2 + 1024;
-    d.cap_csv = std::max<size_t>(2 * C, 1 << 20);
+    // CSV of a chunk that does not fit is produced in groups (worker()): half a chunk holds a whole
+    // chunk of FASTQ or of FASTA reads of >= 100 bp
+    d.cap_csv = std::max<size_t>(C / 2, 1 << 20);
     d.cap_tiles = ((std::max(C / 4096, d.cap_reads / 2048) + 8) | 1) + 1;      // even, so the totals behind it are aligned
-    int rc;
-#define A(call) do { rc = (call); if (rc) return rc; } while (0)
-    A(dmalloc(d.text, C + 256));
-    A(dmalloc(d.line_start, d.cap_lines + 2));
-    A(dmalloc(d.hdr_line, d.cap_reads + 1));
-    A(dmalloc(d.name_s, d.cap_reads)); A(dmalloc(d.name_e, d.cap_reads));
-    A(dmalloc(d.seq_s, d.cap_reads)); A(dmalloc(d.seq_e, d.cap_reads)); A(dmalloc(d.len, d.cap_reads));
-    A(dmalloc(d.reads_ptr, d.cap_reads + 1));
-    A(dmalloc(d.cont, d.cap_cont + 8));
-    A(dmalloc(d.final5, (d.cap_reads + 1) * 5));
-    if (extended) A(dmalloc(d.rows, (d.cap_reads + 1) * (size_t)(2 * row_pairs + 2)));
-    A(dmalloc(d.csv_off, d.cap_reads + 1));
-    A(dmalloc(d.csv, d.cap_csv));
-    A(dmalloc(d.tile_a, d.cap_tiles + 4)); A(dmalloc(d.tile_b, d.cap_tiles + 4));
-    A(dmalloc(d.info, 1));
-#undef A
-    CK(cudaMemset(d.text, '\n', C + 256));
-    CK(cudaMallocHost(&s.h_text, C));
-    CK(cudaMallocHost(&s.h_csv, d.cap_csv));
-    CK(cudaMallocHost(&s.h_info, sizeof(ChunkInfo)));
-    CK(cudaMallocHost(&s.h_counters, N_COUNTERS * sizeof(uint32_t)));
     s.scratch.dense_cap = 1u << 16;
-    CK(cudaMalloc(&s.scratch.d_counters, N_COUNTERS * sizeof(uint32_t)));
-    CK(cudaMalloc(&s.scratch.d_dense_list, (size_t)s.scratch.dense_cap * 4));
-    CK(cudaMemset(s.scratch.d_counters, 0, N_COUNTERS * sizeof(uint32_t)));
+    auto carve_dev = [&](Carver& c) {
+        c.take(d.text, C + 256);
+        c.take(d.line_start, d.cap_lines + 2);
+        c.take(d.hdr_line, d.cap_reads + 1);
+        c.take(d.name_s, d.cap_reads); c.take(d.name_e, d.cap_reads);
+        c.take(d.seq_s, d.cap_reads); c.take(d.seq_e, d.cap_reads); c.take(d.len, d.cap_reads);
+        c.take(d.reads_ptr, d.cap_reads + 1);
+        c.take(d.cont, d.cap_cont + 8);
+        c.take(d.final5, (d.cap_reads + 1) * 5);
+        if (extended) c.take(d.rows, (d.cap_reads + 1) * (size_t)(2 * row_pairs + 2)); else d.rows = nullptr;
+        c.take(d.csv_off, d.cap_reads + 1);
+        c.take(d.csv, d.cap_csv);
+        c.take(d.tile_a, d.cap_tiles + 4); c.take(d.tile_b, d.cap_tiles + 4);
+        c.take(d.info, 1);
+        c.take(s.scratch.d_counters, (size_t)N_COUNTERS);
+        c.take(s.scratch.d_dense_list, (size_t)s.scratch.dense_cap);
+    };
+    auto carve_host = [&](Carver& c) {
+        c.take(s.h_info, 1);
+        c.take(s.h_counters, (size_t)N_COUNTERS);
+        c.take(s.h_csv, d.cap_csv);
+        if (with_stage) c.take(s.h_text, C); else s.h_text = nullptr;
+    };
+    Carver size_d{nullptr}, size_h{nullptr};
+    carve_dev(size_d); carve_host(size_h);
+    CK(cudaMalloc(&s.d_arena, size_d.off + 256));
+    CK(cudaMallocHost(&s.h_arena, size_h.off + 256));
+    Carver cd{static_cast<uint8_t*>(s.d_arena)}, ch{static_cast<uint8_t*>(s.h_arena)};
+    carve_dev(cd); carve_host(ch);
+    s.with_stage = with_stage;
     CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    CK(cudaMemsetAsync(d.text, '\n', C + 256, s.stream));
+    CK(cudaMemsetAsync(s.scratch.d_counters, 0, N_COUNTERS * sizeof(uint32_t), s.stream));
     return CUCLARK_OK;
 }
 
@@ -131,10 +148,6 @@ int ensure_pipe(cuclark_db* db, size_t chunk_bytes, int n_slots, bool extended, 
         db->text_pipe = tp;
         tp->chunk_bytes = chunk_bytes; tp->extended = extended; tp->row_pairs = db->row_pairs;
         tp->slots.resize(n_slots);
-        for (auto& s : tp->slots) {
-            int rc = alloc_slot(s, chunk_bytes, extended, db->row_pairs);
-            if (rc) { text_pipe_free(db); return rc; }
-        }
     }
     // names: [0] = "NA" (src/CuCLARK_hh.hh:1879-1883)
     std::vector<std::string> names;
@@ -192,6 +205,9 @@ struct Job {
     std::string err;
     // totals (guarded by the turn)
     uint64_t n_reads = 0, n_cont = 0, lookups = 0, dense = 0, trunc = 0, n_chunks = 0;
+    // CUCLARK_TIMING=1: seconds per phase, summed over the slot threads (guarded by mu)
+    bool timing = false;
+    double t_phase[7] = {0, 0, 0, 0, 0, 0, 0};   // stage-in, h2d+index, pack, classify+csv, d2h, sink, slot allocation
 
     void fail(int code, const std::string& msg) {
         std::lock_guard<std::mutex> g(mu);
@@ -257,9 +273,46 @@ bool copy_out(Job& J, T* dst, size_t cap, uint64_t at, const void* dsrc, size_t 
     return true;
 }
 
+struct PhaseClock {
+    Job& J;
+    double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+    std::chrono::steady_clock::time_point t;
+    explicit PhaseClock(Job& j) : J(j) { if (J.timing) t = std::chrono::steady_clock::now(); }
+    void lap(int phase) {
+        if (!J.timing) return;
+        const auto n = std::chrono::steady_clock::now();
+        acc[phase] += std::chrono::duration<double>(n - t).count();
+        t = n;
+    }
+    void skip() { if (J.timing) t = std::chrono::steady_clock::now(); }
+    ~PhaseClock() {
+        if (!J.timing) return;
+        std::lock_guard<std::mutex> g(J.mu);
+        for (int i = 0; i < 7; i++) J.t_phase[i] += acc[i];
+    }
+};
+
 void worker(Job& J, cuclark_db* db, TextSlot& S) {
+    PhaseClock pc(J);
     const TextPipe* tp = db->text_pipe;
     if (cudaSetDevice(db->cfg.device) != cudaSuccess) { J.fail(CUCLARK_ERR_CUDA, "cudaSetDevice failed"); return; }
+    if (S.stream && !J.src_pinned && !S.with_stage) free_slot(S);        // allocated for a pinned source earlier
+    if (!S.stream) {
+        {   // nothing left to do? then do not pay for a slot
+            std::lock_guard<std::mutex> g(J.mu);
+            if (J.failed || J.cursor >= J.n) return;
+        }
+        // one slot at a time, in thread order: the driver serialises the allocations anyway, and this way
+        // the first threads are already classifying while the later ones still wait for their memory
+        static std::mutex alloc_mu;
+        int rc;
+        {
+            std::lock_guard<std::mutex> g(alloc_mu);
+            rc = alloc_slot(S, tp->chunk_bytes, tp->extended, tp->row_pairs, !J.src_pinned);
+        }
+        if (rc) { free_slot(S); J.fail(rc, cuclark_last_error()); return; }
+        pc.lap(6);
+    }
     const TextSlotDev& d = S.d;
     const int k = db->cfg.k;
     const size_t pitch = 2 * (size_t)db->row_pairs + 2;
@@ -283,18 +336,22 @@ void worker(Job& J, cuclark_db* db, TextSlot& S) {
         }
         const uint32_t nb = (uint32_t)(end - start);
         const uint8_t* src = J.text + start;
+        pc.skip();
         if (!J.src_pinned) { memcpy(S.h_text, src, nb); src = S.h_text; }
+        pc.lap(0);
         JCK(cudaMemcpyAsync(d.text, src, nb, cudaMemcpyHostToDevice, S.stream));
         JRC(tp_index_launch(d, nb, J.fastq, S.stream));
         JCK(cudaMemcpyAsync(S.h_info, d.info, sizeof(ChunkInfo), cudaMemcpyDeviceToHost, S.stream));
         JCK(cudaStreamSynchronize(S.stream));
         if (S.h_info->err) { J.fail(CUCLARK_ERR_NOMEM, tp_err_text(S.h_info->err)); return; }
         const uint32_t n_reads = S.h_info->n_reads;
+        pc.lap(1);
         JRC(tp_pack_launch(d, nb, n_reads, k, S.stream));
         JCK(cudaMemcpyAsync(S.h_info, d.info, sizeof(ChunkInfo), cudaMemcpyDeviceToHost, S.stream));
         JCK(cudaStreamSynchronize(S.stream));
         if (S.h_info->err) { J.fail(CUCLARK_ERR_NOMEM, tp_err_text(S.h_info->err)); return; }
         const uint64_t n_cont = S.h_info->n_cont;
+        pc.lap(2);
         const bool classify = !J.arrays || J.arrays->final5 || J.arrays->rows;
         if (classify) {
             JRC(classify_launch(db, S.scratch, d.reads_ptr, d.cont, n_reads, d.final5, want_rows ? d.rows : nullptr, S.stream));
@@ -352,11 +409,13 @@ void worker(Job& J, cuclark_db* db, TextSlot& S) {
             if (S.h_info->err) { J.fail(CUCLARK_ERR_NOMEM, tp_err_text(S.h_info->err)); return; }
             if (S.h_counters[COUNTER_DENSE] > S.scratch.dense_cap) { J.fail(CUCLARK_ERR_NOMEM, "too many reads needed the dense fallback"); return; }
             const size_t bytes = S.h_info->csv_bytes;
+            pc.lap(3);
             // the turn only hands out the output offset (file order); the copies of different chunks overlap
             if (!have_turn) { if (!wait_turn(J, seq)) return; have_turn = true; }
             const uint64_t offset = J.out_off;
             J.out_off += bytes;
             if (first + cnt >= n_reads) { account(); end_turn(J); }
+            pc.skip();
             if (!bytes) continue;
             char* dst = S.h_csv;
             if (J.out_buf) {
@@ -365,8 +424,10 @@ void worker(Job& J, cuclark_db* db, TextSlot& S) {
             }
             JCK(cudaMemcpyAsync(dst, d.csv, bytes, cudaMemcpyDeviceToHost, S.stream));
             JCK(cudaStreamSynchronize(S.stream));
+            pc.lap(4);
             if (J.out_buf && !J.out_pinned) memcpy(J.out_buf + offset, S.h_csv, bytes);
             if (J.sink && J.sink(J.user, dst, bytes, offset) != 0) { J.fail(CUCLARK_ERR_IO, "the CSV sink reported an error"); return; }
+            pc.lap(5);
         }
         if (n_reads == 0) {
             if (!wait_turn(J, seq)) return;
@@ -395,7 +456,9 @@ int run_text(cuclark_db* const* dbs, int n_dbs, const uint8_t* text, size_t n, c
         set_error("Failed to recognize the format of the file.");            // src/CuCLARK_hh.hh:1535-1538
         return CUCLARK_ERR_FORMAT;
     }
-    size_t chunk = o && o->chunk_bytes ? o->chunk_bytes : (size_t)64 << 20;
+    // default chunk: small enough that a one-shot run (the CLI) spends little on pinned slot memory and
+    // has many chunks to overlap, large enough to keep the per-chunk synchronisations negligible
+    size_t chunk = o && o->chunk_bytes ? o->chunk_bytes : (n <= ((size_t)4 << 30) ? (size_t)4 << 20 : (size_t)16 << 20);
     chunk = std::min<size_t>(std::max<size_t>(chunk, 4096), (size_t)1 << 30);
     chunk = (chunk + 255) & ~(size_t)255;
     int n_slots = o && o->n_slots > 0 ? o->n_slots : 4;
@@ -406,7 +469,9 @@ int run_text(cuclark_db* const* dbs, int n_dbs, const uint8_t* text, size_t n, c
         int rc = ensure_pipe(dbs[i], chunk, n_slots, extended || (arrays && arrays->rows), o ? o->target_names : nullptr);
         if (rc) return rc;
     }
+    const auto t_setup = std::chrono::steady_clock::now();
     Job J;
+    J.timing = getenv("CUCLARK_TIMING") != nullptr;
     J.text = text; J.n = n;
     J.fastq = text[0] == '@';
     J.paired = o && o->paired; J.extended = extended;
@@ -430,17 +495,27 @@ int run_text(cuclark_db* const* dbs, int n_dbs, const uint8_t* text, size_t n, c
         if (sink && sink(user, h.data(), h.size(), 0) != 0) { set_error("the CSV sink reported an error"); return CUCLARK_ERR_IO; }
         J.out_off = h.size();
     }
-    // one host thread per slot; slots of all devices pull chunks from the same cursor
+    // one host thread per slot; slots of all devices pull chunks from the same cursor. A slot costs
+    // ~10 ms of (serialised) driver time to allocate: short inputs get fewer of them
     const size_t n_chunks_est = (n + chunk - 1) / chunk;
+    const size_t max_threads = std::max<size_t>(std::min<size_t>(n_chunks_est, 2), n_chunks_est / 8);
     std::vector<std::thread> threads;
     size_t started = 0;
-    for (int s = 0; s < n_slots && started < std::max<size_t>(n_chunks_est, 1); s++)
-        for (int i = 0; i < n_dbs && started < std::max<size_t>(n_chunks_est, 1); i++, started++) {
+    for (int s = 0; s < n_slots && started < max_threads; s++)
+        for (int i = 0; i < n_dbs && started < max_threads; i++, started++) {
             cuclark_db* db = dbs[i];
             TextSlot* slot = &db->text_pipe->slots[s];
             threads.emplace_back([&J, db, slot] { worker(J, db, *slot); });
         }
     for (auto& t : threads) t.join();
+    if (J.timing) {
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[cuclark timing] setup %.1f ms, run %.1f ms with %zu threads (%zu chunks of <= %zu MiB); thread-seconds: "
+                        "slot alloc %.3f, stage-in %.3f, h2d+index %.3f, pack %.3f, classify+csv %.3f, d2h %.3f, sink %.3f\n",
+                std::chrono::duration<double, std::milli>(t_setup - t0).count(),
+                std::chrono::duration<double, std::milli>(t1 - t_setup).count(), threads.size(), (size_t)J.n_chunks, chunk >> 20,
+                J.t_phase[6], J.t_phase[0], J.t_phase[1], J.t_phase[2], J.t_phase[3], J.t_phase[4], J.t_phase[5]);
+    }
     if (J.failed) { set_error("%s", J.err.c_str()); return J.rc; }
     dbs[0]->last_lookups = J.lookups; dbs[0]->last_dense = J.dense; dbs[0]->last_trunc = J.trunc;
     if (out) {

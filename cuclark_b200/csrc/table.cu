@@ -7,12 +7,18 @@
 // c = q*HTSIZE + r and scattered ON THE DEVICE into 32-byte sector buckets
 // (layout in common.cuh). The whole table stays resident in HBM: no swap cycles,
 // no 32-bit bucket pointers.
+#include <fcntl.h>
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include <algorithm>
+#include <chrono>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "internal.h"
@@ -25,7 +31,7 @@ namespace {
 constexpr uint32_t ERR_OVF_LIST = 1, ERR_COUNTER = 2, ERR_NO_SLOT = 4;
 constexpr double OVF_LOAD = 0.75;                  // mean entries per 3-slot overflow bucket
 constexpr int CHUNK_THREADS = 1024;
-constexpr uint32_t CHUNK_BLOCKS = 16384;           // 16.7M reference buckets per chunk
+constexpr uint32_t CHUNK_BLOCKS = 8192;            // 8.4M reference buckets per chunk
 
 struct BuildCtx {
     uint4* table;
@@ -502,77 +508,147 @@ void table_free(cuclark_db* db) {
     db->src_bytes[0] = db->src_bytes[1] = db->src_bytes[2] = 0;
 }
 
+// ---- loading <base>.sz/.ky/.lb (or the same three arrays from host memory) ----------------------
+namespace {
+
+// One staging set: a chunk of reference buckets with its keys and labels, host (pinned) and device.
+struct LoadStage {
+    uint8_t *h_sz = nullptr, *h_keep = nullptr, *d_sz = nullptr, *d_keep = nullptr;
+    uint64_t *h_rel = nullptr, *d_rel = nullptr;
+    uint8_t *h_keys = nullptr, *d_keys = nullptr;
+    uint16_t *h_labels = nullptr, *d_labels = nullptr;
+    cudaStream_t st = nullptr;
+    cudaEvent_t done = nullptr;
+    bool busy = false;
+    int init(uint64_t max_buckets, uint64_t max_entries, int kb, bool keep) {
+        CK(cudaMallocHost(&h_sz, max_buckets)); CK(cudaMalloc(&d_sz, max_buckets));
+        if (keep) { CK(cudaMallocHost(&h_keep, max_buckets)); CK(cudaMalloc(&d_keep, max_buckets)); }
+        CK(cudaMallocHost(&h_rel, (CHUNK_BLOCKS + 1) * 8)); CK(cudaMalloc(&d_rel, (CHUNK_BLOCKS + 1) * 8));
+        CK(cudaMallocHost(&h_keys, max_entries * kb)); CK(cudaMalloc(&d_keys, max_entries * kb));
+        CK(cudaMallocHost(&h_labels, max_entries * 2)); CK(cudaMalloc(&d_labels, max_entries * 2));
+        CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+        return CUCLARK_OK;
+    }
+    ~LoadStage() {
+        if (st) cudaStreamSynchronize(st);
+        cudaFreeHost(h_sz); cudaFreeHost(h_keep); cudaFreeHost(h_rel); cudaFreeHost(h_keys); cudaFreeHost(h_labels);
+        cudaFree(d_sz); cudaFree(d_keep); cudaFree(d_rel); cudaFree(d_keys); cudaFree(d_labels);
+        if (done) cudaEventDestroy(done);
+        if (st) cudaStreamDestroy(st);
+    }
+};
+
+bool pread_all(int fd, void* dst, size_t n, uint64_t off) {
+    uint8_t* p = static_cast<uint8_t*>(dst);
+    while (n) {
+        const ssize_t r = pread(fd, p, n, (off_t)off);
+        if (r <= 0) return false;
+        p += r; n -= (size_t)r; off += (uint64_t)r;
+    }
+    return true;
+}
+
+// runs f(t) on n_threads host threads
+template <typename F>
+void parallel_for_threads(int n_threads, F f) {
+    std::vector<std::thread> th;
+    for (int t = 1; t < n_threads; t++) th.emplace_back([&f, t] { f(t); });
+    f(0);
+    for (auto& x : th) x.join();
+}
+
+}  // namespace
+
 int table_build_from_arrays(cuclark_db* db, const uint8_t* sz_in, const void* ky, const uint16_t* lb,
                             uint64_t n_entries_file, int sfactor, const char* base_path) {
     const uint64_t H = db->cfg.htsize;
     const int kb = db->key_bytes;
-    FILE *f_ky = nullptr, *f_lb = nullptr;
-    std::vector<uint8_t> sz_file;
+    const bool timing = getenv("CUCLARK_TIMING") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count(); };
+    // files: .sz is mapped (scanned in place by several threads), .ky/.lb are read chunk by chunk
+    struct Files {
+        int sz = -1, ky = -1, lb = -1;
+        void* map = nullptr; size_t map_n = 0;
+        ~Files() { if (map) munmap(map, map_n); if (sz >= 0) close(sz); if (ky >= 0) close(ky); if (lb >= 0) close(lb); }
+    } fs;
     const uint8_t* sz = sz_in;
     if (base_path) {
-        std::string b(base_path);
-        FILE* f_sz = fopen((b + ".sz").c_str(), "rb");
-        if (!f_sz) { set_error("Failed to open %s.sz", base_path); return CUCLARK_ERR_IO; }
-        f_ky = fopen((b + ".ky").c_str(), "rb");
-        if (!f_ky) { fclose(f_sz); set_error("Failed to open %s.ky", base_path); return CUCLARK_ERR_IO; }
-        f_lb = fopen((b + ".lb").c_str(), "rb");
-        if (!f_lb) { fclose(f_sz); fclose(f_ky); set_error("Failed to open %s.lb", base_path); return CUCLARK_ERR_IO; }
-        sz_file.resize(H);
-        const size_t got = fread(sz_file.data(), 1, H, f_sz);
-        fclose(f_sz);
-        if (got != H) { fclose(f_ky); fclose(f_lb); set_error("%s.sz is short (%zu of %llu bytes)", base_path, got, (unsigned long long)H); return CUCLARK_ERR_IO; }
-        sz = sz_file.data();
+        const std::string b(base_path);
+        fs.sz = open((b + ".sz").c_str(), O_RDONLY);
+        if (fs.sz < 0) { set_error("Failed to open %s.sz", base_path); return CUCLARK_ERR_IO; }
+        fs.ky = open((b + ".ky").c_str(), O_RDONLY);
+        if (fs.ky < 0) { set_error("Failed to open %s.ky", base_path); return CUCLARK_ERR_IO; }
+        fs.lb = open((b + ".lb").c_str(), O_RDONLY);
+        if (fs.lb < 0) { set_error("Failed to open %s.lb", base_path); return CUCLARK_ERR_IO; }
+        struct stat sb;
+        if (fstat(fs.sz, &sb) != 0 || (uint64_t)sb.st_size < H) { set_error("%s.sz is short (%llu of %llu bytes)", base_path, (unsigned long long)sb.st_size, (unsigned long long)H); return CUCLARK_ERR_IO; }
+        fs.map = mmap(nullptr, H, PROT_READ, MAP_PRIVATE, fs.sz, 0);
+        if (fs.map == MAP_FAILED) { fs.map = nullptr; set_error("cannot map %s.sz", base_path); return CUCLARK_ERR_IO; }
+        fs.map_n = H;
+        madvise(fs.map, H, MADV_WILLNEED);
+        sz = static_cast<const uint8_t*>(fs.map);
     }
-    struct Closer { FILE *a, *b; ~Closer() { if (a) fclose(a); if (b) fclose(b); } } closer{f_ky, f_lb};
 
-    // one host pass over the bucket sizes: -s sampling (src/CuClarkDB.cu:511-524),
-    // kept-entry count, and the file offset of every 1024th bucket
+    // host pass over the bucket sizes, on several threads: entries before every 1024-bucket block,
+    // -s sampling (src/CuClarkDB.cu:511-524: of the non-empty buckets numbered 1,2,3... keep every
+    // sfactor-th) and the kept-entry count
     const uint64_t n_blocks = (H + CHUNK_THREADS - 1) / CHUNK_THREADS;
     std::vector<uint64_t> coarse(n_blocks + 1);
     std::vector<uint8_t> keep;
     if (sfactor > 1) keep.assign(H, 0);
-    uint64_t total = 0, kept = 0, nonzero = 0;
-    for (uint64_t r = 0; r < H; r++) {
-        if ((r % CHUNK_THREADS) == 0) coarse[r / CHUNK_THREADS] = total;
-        const uint32_t s = sz[r];
-        if (!s) continue;
-        nonzero++;
-        total += s;
+    const int n_thr = (int)std::max<uint64_t>(1, std::min<uint64_t>({(uint64_t)std::thread::hardware_concurrency(), 16, n_blocks / 64 + 1}));
+    std::vector<uint64_t> part_total(n_thr + 1, 0), part_nonzero(n_thr + 1, 0), part_kept(n_thr, 0);
+    auto block_range = [&](int t, uint64_t& b0, uint64_t& b1) { b0 = n_blocks * t / n_thr; b1 = n_blocks * (t + 1) / n_thr; };
+    parallel_for_threads(n_thr, [&](int t) {
+        uint64_t b0, b1; block_range(t, b0, b1);
+        uint64_t total = 0, nonzero = 0;
+        for (uint64_t bk = b0; bk < b1; bk++) {
+            coarse[bk] = total;                                   // relative to the thread's range; rebased below
+            const uint64_t r1 = std::min<uint64_t>((bk + 1) * CHUNK_THREADS, H);
+            for (uint64_t r = bk * CHUNK_THREADS; r < r1; r++) { total += sz[r]; nonzero += sz[r] != 0; }
+        }
+        part_total[t + 1] = total; part_nonzero[t + 1] = nonzero;
+    });
+    for (int t = 0; t < n_thr; t++) { part_total[t + 1] += part_total[t]; part_nonzero[t + 1] += part_nonzero[t]; }
+    const uint64_t total = part_total[n_thr];
+    parallel_for_threads(n_thr, [&](int t) {
+        uint64_t b0, b1; block_range(t, b0, b1);
+        for (uint64_t bk = b0; bk < b1; bk++) coarse[bk] += part_total[t];
         if (sfactor > 1) {
-            if ((nonzero % (uint64_t)sfactor) == 0) { keep[r] = 1; kept += s; }
-        } else kept += s;
-    }
+            uint64_t nonzero = part_nonzero[t], kept = 0;
+            const uint64_t r1 = std::min<uint64_t>(b1 * CHUNK_THREADS, H);
+            for (uint64_t r = b0 * CHUNK_THREADS; r < r1; r++) {
+                if (!sz[r]) continue;
+                if ((++nonzero % (uint64_t)sfactor) == 0) { keep[r] = 1; kept += sz[r]; }
+            }
+            part_kept[t] = kept;
+        }
+    });
     coarse[n_blocks] = total;
+    uint64_t kept = total;
+    if (sfactor > 1) { kept = 0; for (int t = 0; t < n_thr; t++) kept += part_kept[t]; }
     db->src_sfactor = sfactor > 1 ? sfactor : 1;
     db->src_bytes[0] = base_path ? H : 0;
     db->src_bytes[1] = base_path ? total * (uint64_t)kb : 0;
     db->src_bytes[2] = base_path ? total * 2 : 0;
     if (!base_path && total != n_entries_file) { set_error("bucket sizes sum to %llu entries but %llu were passed", (unsigned long long)total, (unsigned long long)n_entries_file); return CUCLARK_ERR_ARG; }
+    const double ms_scan = since(t_begin);
+    const auto t_build = std::chrono::steady_clock::now();
 
-    // largest chunk, for the staging buffers
-    uint64_t max_chunk_entries = 0;
+    // largest chunk, for the staging sets
+    uint64_t max_chunk_entries = 1;
     for (uint64_t b0 = 0; b0 < n_blocks; b0 += CHUNK_BLOCKS) {
         const uint64_t b1 = std::min<uint64_t>(b0 + CHUNK_BLOCKS, n_blocks);
         max_chunk_entries = std::max(max_chunk_entries, coarse[b1] - coarse[b0]);
     }
     const uint64_t max_chunk_buckets = std::min<uint64_t>((uint64_t)CHUNK_BLOCKS * CHUNK_THREADS, H);
-
-    uint8_t *d_sz = nullptr, *d_keep = nullptr;
-    uint64_t* d_coarse = nullptr;
-    void* d_keys = nullptr;
-    uint16_t* d_labels = nullptr;
-    void* h_stage = nullptr;
-    auto free_stage = [&]() {
-        cudaFree(d_sz); cudaFree(d_keep); cudaFree(d_coarse); cudaFree(d_keys); cudaFree(d_labels);
-        if (h_stage) cudaFreeHost(h_stage);
-        d_sz = d_keep = nullptr; d_coarse = nullptr; d_keys = nullptr; d_labels = nullptr; h_stage = nullptr;
-    };
-    CK(cudaMalloc(&d_sz, max_chunk_buckets));
-    if (sfactor > 1) CK(cudaMalloc(&d_keep, max_chunk_buckets));
-    CK(cudaMalloc(&d_coarse, (CHUNK_BLOCKS + 1) * 8));
-    CK(cudaMalloc(&d_keys, std::max<uint64_t>(max_chunk_entries, 1) * kb));
-    CK(cudaMalloc(&d_labels, std::max<uint64_t>(max_chunk_entries, 1) * 2));
-    if (base_path) CK(cudaMallocHost(&h_stage, std::max<uint64_t>(max_chunk_entries, 1) * std::max(kb, 2)));
+    LoadStage stage[2];
+    for (auto& s : stage) {
+        const int rc = s.init(max_chunk_buckets, max_chunk_entries, kb, sfactor > 1);
+        if (rc) return rc;
+    }
 
     int rc = CUCLARK_ERR_BUILD;
     double grow = 1.0;
@@ -582,45 +658,62 @@ int table_build_from_arrays(cuclark_db* db, const uint8_t* sz_in, const void* ky
         BuildCtx x{};
         rc = alloc_build(g, kept / (db->cfg.shard_count > 1 ? db->cfg.shard_count : 1), bb, x, H);
         if (rc != CUCLARK_OK) { bb.free_all(); break; }
-        if (base_path) { fseek(f_ky, 0, SEEK_SET); fseek(f_lb, 0, SEEK_SET); }
-        std::vector<uint64_t> rel(CHUNK_BLOCKS + 1);
+        if (cudaDeviceSynchronize() != cudaSuccess) {              // the table is initialised on the default stream
+            set_error("table initialisation failed: %s", cudaGetErrorString(cudaGetLastError()));
+            bb.free_all();
+            return CUCLARK_ERR_CUDA;
+        }
+        uint64_t n_chunk = 0;
         for (uint64_t b0 = 0; b0 < n_blocks && rc == CUCLARK_OK; b0 += CHUNK_BLOCKS) {
             const uint64_t b1 = std::min<uint64_t>(b0 + CHUNK_BLOCKS, n_blocks);
             const uint64_t r0 = b0 * CHUNK_THREADS, r1 = std::min<uint64_t>(b1 * CHUNK_THREADS, H);
             const uint64_t e0 = coarse[b0], ne = coarse[b1] - e0;
             if (ne == 0) continue;
-            for (uint64_t b = b0; b <= b1; b++) rel[b - b0] = coarse[b] - e0;
-            auto cp = [&](void* dst, const void* src, size_t n) { return cudaMemcpy(dst, src, n, cudaMemcpyHostToDevice); };
-            cudaError_t e = cp(d_sz, sz + r0, r1 - r0);
-            if (e == cudaSuccess && sfactor > 1) e = cp(d_keep, keep.data() + r0, r1 - r0);
-            if (e == cudaSuccess) e = cp(d_coarse, rel.data(), (b1 - b0 + 1) * 8);
+            // the host fills one staging set while the device works on the other
+            LoadStage& S = stage[n_chunk++ & 1];
+            cudaError_t e = S.busy ? cudaEventSynchronize(S.done) : cudaSuccess;
             if (e == cudaSuccess) {
+                memcpy(S.h_sz, sz + r0, r1 - r0);
+                if (sfactor > 1) memcpy(S.h_keep, keep.data() + r0, r1 - r0);
+                for (uint64_t b = b0; b <= b1; b++) S.h_rel[b - b0] = coarse[b] - e0;
                 if (base_path) {
-                    if (fread(h_stage, kb, ne, f_ky) != ne) { set_error("%s.ky is short", base_path); rc = CUCLARK_ERR_IO; break; }
-                    e = cp(d_keys, h_stage, ne * kb);
-                    if (e == cudaSuccess) {
-                        if (fread(h_stage, 2, ne, f_lb) != ne) { set_error("%s.lb is short", base_path); rc = CUCLARK_ERR_IO; break; }
-                        e = cp(d_labels, h_stage, ne * 2);
-                    }
+                    if (!pread_all(fs.ky, S.h_keys, ne * kb, e0 * kb)) { set_error("%s.ky is short", base_path); rc = CUCLARK_ERR_IO; break; }
+                    if (!pread_all(fs.lb, S.h_labels, ne * 2, e0 * 2)) { set_error("%s.lb is short", base_path); rc = CUCLARK_ERR_IO; break; }
                 } else {
-                    e = cp(d_keys, static_cast<const uint8_t*>(ky) + e0 * kb, ne * kb);
-                    if (e == cudaSuccess) e = cp(d_labels, lb + e0, ne * 2);
+                    memcpy(S.h_keys, static_cast<const uint8_t*>(ky) + e0 * kb, ne * kb);
+                    memcpy(S.h_labels, lb + e0, ne * 2);
                 }
+                auto cp = [&](void* dst, const void* src, size_t n) { return cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, S.st); };
+                e = cp(S.d_sz, S.h_sz, r1 - r0);
+                if (e == cudaSuccess && sfactor > 1) e = cp(S.d_keep, S.h_keep, r1 - r0);
+                if (e == cudaSuccess) e = cp(S.d_rel, S.h_rel, (b1 - b0 + 1) * 8);
+                if (e == cudaSuccess) e = cp(S.d_keys, S.h_keys, ne * kb);
+                if (e == cudaSuccess) e = cp(S.d_labels, S.h_labels, ne * 2);
             }
             if (e != cudaSuccess) { set_error("DB upload failed: %s", cudaGetErrorString(e)); rc = CUCLARK_ERR_CUDA; break; }
             const unsigned blocks = (unsigned)(b1 - b0);
             if (g.layout == LAYOUT_NARROW)
-                k_insert_chunk<LAYOUT_NARROW><<<blocks, CHUNK_THREADS>>>(x, d_sz, d_keep, d_coarse, r0, (uint32_t)(r1 - r0), d_keys, d_labels, kb);
+                k_insert_chunk<LAYOUT_NARROW><<<blocks, CHUNK_THREADS, 0, S.st>>>(x, S.d_sz, S.d_keep, S.d_rel, r0, (uint32_t)(r1 - r0), S.d_keys, S.d_labels, kb);
             else
-                k_insert_chunk<LAYOUT_WIDE><<<blocks, CHUNK_THREADS>>>(x, d_sz, d_keep, d_coarse, r0, (uint32_t)(r1 - r0), d_keys, d_labels, kb);
+                k_insert_chunk<LAYOUT_WIDE><<<blocks, CHUNK_THREADS, 0, S.st>>>(x, S.d_sz, S.d_keep, S.d_rel, r0, (uint32_t)(r1 - r0), S.d_keys, S.d_labels, kb);
             e = cudaGetLastError();
-            if (e == cudaSuccess) e = cudaDeviceSynchronize();   // staging buffers are reused
+            if (e == cudaSuccess) e = cudaEventRecord(S.done, S.st);
             if (e != cudaSuccess) { set_error("insert kernel failed: %s", cudaGetErrorString(e)); rc = CUCLARK_ERR_CUDA; break; }
+            S.busy = true;
+        }
+        for (auto& S : stage) {
+            if (!S.busy) continue;
+            const cudaError_t e = cudaStreamSynchronize(S.st);
+            S.busy = false;
+            if (e != cudaSuccess && rc == CUCLARK_OK) { set_error("insert kernel failed: %s", cudaGetErrorString(e)); rc = CUCLARK_ERR_CUDA; }
         }
         if (rc == CUCLARK_OK) rc = finish_build(db, g, bb, x, false);
         if (rc != CUCLARK_OK) bb.free_all();
     }
-    free_stage();
+    if (timing)
+        fprintf(stderr, "[cuclark timing] database load: host pass over %llu bucket sizes %.1f ms on %d threads, "
+                        "upload + device re-bucketing of %llu entries %.1f ms\n",
+                (unsigned long long)H, ms_scan, n_thr, (unsigned long long)kept, since(t_build));
     return rc;
 }
 

@@ -187,7 +187,7 @@ typedef struct cuclark_text_opts {
     int paired;                        /* Length column = Length - 1: mates joined by one N (:2112)  */
     int extended;                      /* --extended: one hit-count column per target (:2014-2031)   */
     const char* const* target_names;   /* n_targets labels in label order (NULL: "T<i>")             */
-    size_t chunk_bytes;                /* text bytes per chunk; 0 = 64 MiB                           */
+    size_t chunk_bytes;                /* text bytes per chunk; 0 = 4 MiB (16 MiB above 4 GiB input) */
     int n_slots;                       /* chunks in flight (host threads, streams); 0 = 4            */
 } cuclark_text_opts;
 
