@@ -28,6 +28,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -603,7 +604,17 @@ extern "C" int cuclark_build_database(const cuclark_build_opts* o, const char* c
         return CUCLARK_ERR_NO_DEVICE;
     }
     if (o->device < 0 || o->device >= n_dev) { set_error("device %d not present", o->device); return CUCLARK_ERR_NO_DEVICE; }
+    const bool timing = getenv("CUCLARK_TIMING") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        const auto n = std::chrono::steady_clock::now();
+        fprintf(stderr, "[cuclark timing] database build: %s %.1f ms\n", what, std::chrono::duration<double, std::milli>(n - t_last).count());
+        t_last = n;
+    };
     CK(cudaSetDevice(o->device));
+    CK(cudaFree(nullptr));
+    lap("CUDA context");
     if (stats) memset(stats, 0, sizeof *stats);
     const int k = o->k;
     const uint64_t htsize = o->htsize;
@@ -662,6 +673,7 @@ extern "C" int cuclark_build_database(const cuclark_build_opts* o, const char* c
             B(cudaStreamSynchronize(st));
         }
         n_nt = nt_pass;
+        lap(pass == 0 ? "pass 1 over the targets (count)" : "pass 2 over the targets (scatter)");
         if (pass == 0) {
             uint64_t* d_total = tile_base + n_seg_tiles;
             k_db_tile_offsets<<<(uint32_t)n_seg_tiles, DBT, 0, st>>>(count, htsize, local, tile_base);
@@ -685,6 +697,7 @@ extern "C" int cuclark_build_database(const cuclark_build_opts* o, const char* c
     else
         rc = reduce_and_write<uint32_t>((uint32_t*)keys, labels, local, tile_base, count, out_local, out_tile, n_seg_tiles, htsize,
                                         o->min_count, total, key_bytes, out_base, d_err, &total_kept, st);
+    lap("per-bucket sort, RemoveCommon and file write");
     if (stats) {
         stats->n_nucleotides = n_nt;
         stats->n_kmers_added = total;
