@@ -59,6 +59,9 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--chunk-mb", type=int, default=64, help="text pipeline: MiB of text per chunk")
     ap.add_argument("--slots", type=int, default=4, help="text pipeline: chunks in flight")
+    ap.add_argument("--layout", type=int, default=int(os.environ.get("CUCLARK_BENCH_LAYOUT", 0)),
+                    help="device table layout: 0 auto, 1 narrow, 2 wide, 3 local (minimizer-addressed lines)")
+    ap.add_argument("--load", type=float, default=0.0, help="entries per bucket (0 = the layout's default)")
     ap.add_argument("--mode", default="read", choices=["read", "table"],
                     help="multi-GPU mode: read-partitioned/replicated table, or table-partitioned + NCCL row exchange")
     return ap.parse_args()
@@ -229,7 +232,8 @@ def run_b200(args):
 
     n, T = args.reads, args.targets
     table_mode = args.mode == "table" and world > 1
-    g = CuClarkDB(K, T, htsize=HTSIZE_FULL, device=local, shard=(rank, world) if table_mode else (0, 1))
+    g = CuClarkDB(K, T, htsize=HTSIZE_FULL, device=local, shard=(rank, world) if table_mode else (0, 1),
+                  layout=args.layout, bucket_load=args.load)
     t0 = time.time()
     g.build_synthetic(DB_SEED, T, GENOME_LEN, 0)
     build_s = time.time() - t0
@@ -404,11 +408,11 @@ def run_b200(args):
             "reads_per_s": reads_all * args.steps / (total_ms_max * 1e-3),
             "config": workload_config(args, world),
             "table": {"entries": st["n_entries"], "buckets": st["n_buckets"], "bytes": st["table_bytes"],
-                      "layout": "narrow" if st["layout"] == 1 else "wide", "overflow_entries": st["n_spilled"],
+                      "layout": {1: "narrow", 2: "wide", 3: "local"}.get(st["layout"], str(st["layout"])), "overflow_entries": st["n_spilled"],
                       "overflowed_buckets": st["n_spill_buckets"], "build_s": build_s},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic("config2", lookups), "algorithmic_bytes": lookups * BYTES_PER_LOOKUP, "peak_source": peak_src,
-                         "kernel": "k_classify<NARROW,false>", "kernel_ms": kernel_ms,
+                         "traffic": ncu_traffic("config2" if st["layout"] == 1 else "config2_layout%d" % st["layout"], lookups), "algorithmic_bytes": lookups * BYTES_PER_LOOKUP, "peak_source": peak_src,
+                         "kernel": "k_classify<%s,false>" % {1: "NARROW", 2: "WIDE", 3: "LOCAL"}.get(st["layout"], "?"), "kernel_ms": kernel_ms,
                          "bytes_per_lookup": BYTES_PER_LOOKUP, "lookups_per_launch": lookups,
                          "random_access_peak": random_gbs, "frac_random_access": achieved / random_gbs,
                          "random_access_peak_source": "measured live: 2^28 random 32 B sector loads over the same table"},

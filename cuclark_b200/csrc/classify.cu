@@ -30,6 +30,14 @@ namespace {
 constexpr int WARPS_PER_BLOCK = 8;
 constexpr int TSLOTS = 64;            // per-warp hash slots
 constexpr int ILP_ROUNDS = 4;         // independent probes per lane
+#ifndef CUCLARK_ILP_LOCAL
+#define CUCLARK_ILP_LOCAL 2
+#endif
+#ifndef CUCLARK_LOCAL_MIN_BLOCKS
+#define CUCLARK_LOCAL_MIN_BLOCKS 4
+#endif
+constexpr int ILP_LOCAL = CUCLARK_ILP_LOCAL;                // LOCAL layout: rows per group (more resident warps instead)
+constexpr int LOCAL_MIN_BLOCKS = CUCLARK_LOCAL_MIN_BLOCKS;  // resident blocks per SM asked of ptxas for the LOCAL kernel
 constexpr int CHUNK_ROUNDS = 31;      // rounds of 32 k-mers served by one set of 32 words
 constexpr int MAX_ROW_PAIRS = 63;
 constexpr uint32_t EMPTY = 0xFFFFFFFFu;
@@ -86,7 +94,7 @@ __device__ __forceinline__ uint64_t assemble_words(const uint32_t (&wv)[4], int 
 }
 
 template <int LAYOUT, bool ROWS>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_classify(const ClassifyParams p) {
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, LAYOUT == LAYOUT_LOCAL ? LOCAL_MIN_BLOCKS : 2) k_classify(const ClassifyParams p) {
     __shared__ uint32_t s_key[WARPS_PER_BLOCK][TSLOTS];
     __shared__ uint32_t s_cnt[WARPS_PER_BLOCK][TSLOTS];
     __shared__ uint16_t s_row[ROWS ? WARPS_PER_BLOCK : 1][ROWS ? 2 * MAX_ROW_PAIRS + 2 : 2];
@@ -98,6 +106,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_classify(const Classif
     tcnt[lane] = 0; tcnt[lane + 32] = 0;
     __syncwarp();
 
+    constexpr int ILP = LAYOUT == LAYOUT_LOCAL ? ILP_LOCAL : ILP_ROUNDS;
     const TableView& T = p.t;
     const int k = T.k;
     const int kshift = 64 - 2 * k;
@@ -139,6 +148,25 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_classify(const Classif
             uint32_t first_label = NO_LABEL, first_cnt = 0, total = 0;
             bool table_mode = false, overflow = false;
             bool first_part = true;
+            // hits of one row of 32 k-mers into the read's counters (warp-collective)
+            auto account = [&](const uint32_t label) {
+                const uint32_t hitmask = __ballot_sync(0xFFFFFFFFu, label != NO_LABEL);
+                if (!hitmask) return;
+                total += __popc(hitmask);
+                if (!table_mode) {
+                    if (first_label == NO_LABEL) first_label = __shfl_sync(0xFFFFFFFFu, label, __ffs(hitmask) - 1);
+                    const uint32_t same = __ballot_sync(0xFFFFFFFFu, label == first_label);
+                    if (same == hitmask) { first_cnt += __popc(same); return; }
+                    table_mode = true;
+                    if (lane == 0 && first_cnt) tab_add(tkey, tcnt, first_label, first_cnt);
+                    __syncwarp();
+                }
+                const uint32_t grp = __match_any_sync(0xFFFFFFFFu, label);
+                bool ok = true;
+                if (label != NO_LABEL && lane == __ffs(grp) - 1) ok = tab_add(tkey, tcnt, label, __popc(grp));
+                if (__any_sync(0xFFFFFFFFu, !ok)) overflow = true;
+                __syncwarp();
+            };
 
             while (pos < end) {
                 const uint32_t L = first_part ? cur_hdr : (uint32_t)p.cont[pos];
@@ -159,51 +187,161 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_classify(const Classif
                     }
                     const uint64_t W = assemble_words(wv, nwin, lane);
                     const int rounds = min(CHUNK_ROUNDS, (nk - cb + 31) >> 5);
-                    for (int r0 = 0; r0 < rounds; r0 += ILP_ROUNDS) {
-                        uint64_t q[ILP_ROUNDS];
-                        uint32_t lb[ILP_ROUNDS];
-                        Sector sec[ILP_ROUNDS];
-                        bool live[ILP_ROUNDS];
+                    bool have_carry = false;                 // LOCAL: hash row handed over from the previous group
+                    uint64_t carry_z = 0, carry_x = 0, carry_rc = 0;
+                    uint32_t carry_oh = 0;
+                    const int m_limit = (int)L - (k - LOCAL_W + 1) - cb - lane;   // an m-mer starts at row i iff 32 i <= m_limit
+                    for (int r0 = 0; r0 < rounds; r0 += ILP) {
+                        uint64_t q[ILP];
+                        uint32_t lb[ILP];
+                        Sector sec[ILP];
+                        bool live[ILP];
+                        uint64_t cc[LAYOUT == LAYOUT_LOCAL ? ILP : 1];   // LOCAL: the k-mer itself (overflow key)
+                        if (LAYOUT == LAYOUT_LOCAL) {
+                            // ---- minimizer of every k-mer of the ILP rows. Each lane hashes the FIRST m-mer of
+                            // its position (rows r0..r0+ILP: the windows of the last row reach 7 positions
+                            // into the next one); a windowed minimum over 8 consecutive positions by doubling
+                            // across lanes gives every k-mer its minimizer. Two minima are kept: leftmost
+                            // and rightmost position of the smallest hash, because "leftmost in the
+                            // canonical orientation" is the rightmost one of a read showing the reverse strand.
+                            constexpr int NR = ILP + 1;
+                            const int m = k - LOCAL_W + 1, mbits = 2 * m;
+                            const uint64_t mmask = (~0ull) >> (64 - mbits);
+                            uint64_t xs[ILP], rcs[ILP];
+                            uint64_t zs[NR];                  // mixed canonical m-mer | (a < b) << 63 | (a > b) << 62
+                            uint32_t AL[NR], AR[NR];
 #pragma unroll
-                        for (int j = 0; j < ILP_ROUNDS; j++) {
-                            const int i = r0 + j;
-                            const uint64_t hi = shfl64(W, i & 31), lo = shfl64(W, (i + 1) & 31);
-                            uint64_t x = lane ? ((hi << (2 * lane)) | (lo >> (64 - 2 * lane))) : hi;
-                            x >>= kshift;
-                            const bool valid = i < rounds && cb + 32 * i + lane < nk;
-                            uint64_t b;
-                            divmod_M(canonical(x, k), T.M, T.magic, q[j], b);
-                            const uint64_t lb64 = b - T.lo;
-                            lb[j] = (uint32_t)lb64;              // n_local < 2^32 (checked at build)
-                            live[j] = valid && lb64 < T.n_local;
-                            my_lookups += valid;
-                            if (live[j]) sec[j] = load_sector(T.buckets + 2 * (uint64_t)lb[j]);
-                        }
+                            for (int R = 0; R < NR; R++) {
+                                const int i = r0 + R;
+                                uint64_t x, rc;
+                                uint32_t oh;
+                                if (R == 0 && have_carry) {           // warp-uniform: the previous group's tail row
+                                    x = carry_x; rc = carry_rc; zs[R] = carry_z; oh = carry_oh;
+                                } else {
+                                    const uint64_t hi = shfl64(W, i & 31), lo = shfl64(W, (i + 1) & 31);
+                                    x = lane ? ((hi << (2 * lane)) | (lo >> (64 - 2 * lane))) : hi;
+                                    x >>= kshift;
+                                    rc = revcomp2(x, k);
+                                    // first m-mer of x and its reverse complement (= last m-mer of rc); the x of a
+                                    // row past the 32 words has undefined low bits, which neither of the two touches
+                                    const uint64_t a = x >> (2 * (LOCAL_W - 1)), b = rc & mmask;
+                                    const bool lt = a < b;
+                                    const uint64_t z = local_mix(lt ? a : b, mbits);
+                                    oh = local_order(z, mbits);
+                                    if (i > 31 || 32 * i > m_limit) oh = LOCAL_ORDER_MAX + 1;   // no m-mer here
+                                    zs[R] = z | ((uint64_t)lt << 63) | ((uint64_t)(!lt && a != b) << 62);
+                                }
+                                if (R < ILP) { xs[R < ILP ? R : 0] = x; rcs[R < ILP ? R : 0] = rc; }
+                                if (R == NR - 1) { carry_x = x; carry_rc = rc; carry_z = zs[R]; carry_oh = oh; }
+                                AL[R] = (oh << 8) | (uint32_t)(32 * R + lane);
+                                AR[R] = (oh << 8) | (uint32_t)(255 - (32 * R + lane));
+                            }
+                            have_carry = true;
 #pragma unroll
-                        for (int j = 0; j < ILP_ROUNDS; j++) {
-                            uint32_t label = NO_LABEL;
-                            if (live[j]) {
-                                label = match_sector<LAYOUT>(sec[j], q[j]);
-                                if (label == NO_LABEL && sector_overflowed(sec[j]))
-                                    label = ovf_lookup(T, q[j] * T.M + ((uint64_t)lb[j] + T.lo));
-                                if (label >= p.n_targets) label = NO_LABEL;
+                            for (int lvl = 0; lvl < 3; lvl++) {            // windows 2, 4, 8
+                                const int sft = 1 << lvl;
+                                const int src = (lane + sft) & 31;
+                                const bool wrap = lane + sft >= 32;
+                                uint32_t TL[NR], TR[NR];
+#pragma unroll
+                                for (int R = 0; R < NR; R++) {
+                                    TL[R] = __shfl_sync(0xFFFFFFFFu, AL[R], src);
+                                    TR[R] = __shfl_sync(0xFFFFFFFFu, AR[R], src);
+                                }
+#pragma unroll
+                                for (int R = 0; R < NR; R++) {
+                                    // (lanes near 31 of the last row take wrapped values: nobody reads them)
+                                    AL[R] = min(AL[R], (wrap && R + 1 < NR) ? TL[R + 1 < NR ? R + 1 : R] : TL[R]);
+                                    AR[R] = min(AR[R], (wrap && R + 1 < NR) ? TR[R + 1 < NR ? R + 1 : R] : TR[R]);
+                                }
                             }
-                            const uint32_t hitmask = __ballot_sync(0xFFFFFFFFu, label != NO_LABEL);
-                            if (!hitmask) continue;
-                            total += __popc(hitmask);
-                            if (!table_mode) {
-                                if (first_label == NO_LABEL) first_label = __shfl_sync(0xFFFFFFFFu, label, __ffs(hitmask) - 1);
-                                const uint32_t same = __ballot_sync(0xFFFFFFFFu, label == first_label);
-                                if (same == hitmask) { first_cnt += __popc(same); continue; }
-                                table_mode = true;
-                                if (lane == 0 && first_cnt) tab_add(tkey, tcnt, first_label, first_cnt);
-                                __syncwarp();
+#pragma unroll
+                            for (int j = 0; j < ILP; j++) {
+                                const int i = r0 + j;
+                                const bool valid = i < rounds && cb + 32 * i + lane < nk;
+                                const uint64_t x = xs[j], rc = rcs[j];
+                                const bool is_fwd = x <= rc;
+                                const uint64_t c = is_fwd ? x : rc;
+                                const uint32_t pos = is_fwd ? (AL[j] & 255u) : 255u - (AR[j] & 255u);   // 32 j + lane + offset
+                                const int src = (int)(pos & 31u);
+                                const uint64_t z0 = shfl64(zs[j], src), z1 = shfl64(zs[j + 1], src);
+                                const uint64_t zf = (pos >> 5) == (uint32_t)j ? z0 : z1;
+                                const int o_read = (int)((pos - (uint32_t)(32 * j + lane)) & 7u);
+                                uint64_t zq, line;
+                                divmod_M(zf & ((1ull << 62) - 1), T.NL, T.magicNL, zq, line);
+                                const int o_c = is_fwd ? o_read : LOCAL_W - 1 - o_read;
+                                const bool f = (zf >> (is_fwd ? 63 : 62)) & 1ull;
+                                const uint32_t rest = local_rest(c, o_c, m);
+                                q[j] = (uint64_t)local_key_lo(zq, rest) | ((uint64_t)local_key_hi(rest, o_c, f) << 32);
+                                cc[j] = c;
+                                const uint64_t lb64 = line * 4 + (uint64_t)(o_c & 3) - T.lo;
+                                lb[j] = (uint32_t)lb64;
+                                live[j] = valid && lb64 < T.n_local;
+                                my_lookups += valid;
+                                if (live[j]) sec[j] = load_sector_line(T.buckets + 2 * (uint64_t)lb[j]);
                             }
-                            const uint32_t grp = __match_any_sync(0xFFFFFFFFu, label);
-                            bool ok = true;
-                            if (label != NO_LABEL && lane == __ffs(grp) - 1) ok = tab_add(tkey, tcnt, label, __popc(grp));
-                            if (__any_sync(0xFFFFFFFFu, !ok)) overflow = true;
-                            __syncwarp();
+                            // Home sectors are consumed row by row (the hit accounting of row j runs while the
+                            // loads of the later rows are still in flight); a lane whose k-mer may have spilled
+                            // issues its first overflow probe at once and counts as "no hit" for now. The
+                            // overflow probes are consumed in a second sweep: hit counts are additive, so a
+                            // row may be accounted in two parts. (The clumped fill of the lines spills ~15% of
+                            // the entries; probing them one after the other would cost a round trip each.)
+                            bool need[ILP];
+                            uint64_t ob[ILP];
+#pragma unroll
+                            for (int j = 0; j < ILP; j++) {
+                                uint32_t label = NO_LABEL;
+                                need[j] = false;
+                                if (live[j]) {
+                                    label = match_sector<LAYOUT_LOCAL>(sec[j], q[j]);
+                                    need[j] = label == NO_LABEL && sector_overflowed(sec[j]);
+                                    if (label >= p.n_targets) label = NO_LABEL;
+                                }
+                                if (need[j]) {
+                                    ob[j] = ovf_home(cc[j], T.n_ovf);
+                                    sec[j] = load_sector(T.ovf + 2 * ob[j]);
+                                }
+                                account(label);
+                            }
+#pragma unroll
+                            for (int j = 0; j < ILP; j++) {
+                                if (!__any_sync(0xFFFFFFFFu, need[j])) continue;
+                                uint32_t label = NO_LABEL;
+                                if (need[j]) {
+                                    label = match_sector<LAYOUT_WIDE>(sec[j], cc[j]);
+                                    if (label == NO_LABEL && ((uint64_t)sec[j].w[4] | ((uint64_t)sec[j].w[5] << 32)) != OVF_EMPTY)
+                                        label = ovf_lookup_from(T, cc[j], ob[j] + 1 == T.n_ovf ? 0 : ob[j] + 1, 1);
+                                    if (label >= p.n_targets) label = NO_LABEL;
+                                }
+                                account(label);
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < ILP; j++) {
+                                const int i = r0 + j;
+                                const uint64_t hi = shfl64(W, i & 31), lo = shfl64(W, (i + 1) & 31);
+                                uint64_t x = lane ? ((hi << (2 * lane)) | (lo >> (64 - 2 * lane))) : hi;
+                                x >>= kshift;
+                                const bool valid = i < rounds && cb + 32 * i + lane < nk;
+                                uint64_t b;
+                                divmod_M(canonical(x, k), T.M, T.magic, q[j], b);
+                                const uint64_t lb64 = b - T.lo;
+                                lb[j] = (uint32_t)lb64;              // n_local < 2^32 (checked at build)
+                                live[j] = valid && lb64 < T.n_local;
+                                my_lookups += valid;
+                                if (live[j]) sec[j] = load_sector(T.buckets + 2 * (uint64_t)lb[j]);
+                            }
+#pragma unroll
+                            for (int j = 0; j < ILP; j++) {
+                                uint32_t label = NO_LABEL;
+                                if (live[j]) {
+                                    label = match_sector<LAYOUT>(sec[j], q[j]);
+                                    if (label == NO_LABEL && sector_overflowed(sec[j]))
+                                        label = ovf_lookup(T, q[j] * T.M + ((uint64_t)lb[j] + T.lo));
+                                    if (label >= p.n_targets) label = NO_LABEL;
+                                }
+                                account(label);
+                            }
                         }
                     }
                 }
@@ -529,30 +667,24 @@ int classify_launch(cuclark_db* db, const Scratch& sc, const uint32_t* d_ptr, co
     p.counters = sc.d_counters; p.dense_list = sc.d_dense_list; p.dense_cap = sc.dense_cap;
     CK(cudaMemsetAsync(sc.d_counters, 0, N_COUNTERS * sizeof(uint32_t), st));
     if (n_reads == 0) return CUCLARK_OK;
-    const bool narrow = db->view.layout == LAYOUT_NARROW;
+    const int layout = db->view.layout;
+    const bool narrow = layout == LAYOUT_NARROW, local = layout == LAYOUT_LOCAL;
     // persistent grid: SM count x resident blocks per SM (one wave), capped by the work
-    const int variant = (narrow ? 0 : 2) + (d_rows ? 1 : 0);
-    if (!db->classify_blocks_per_sm[variant]) {
-        int n;
-        if (d_rows) n = narrow ? blocks_per_sm(k_classify<LAYOUT_NARROW, true>) : blocks_per_sm(k_classify<LAYOUT_WIDE, true>);
-        else n = narrow ? blocks_per_sm(k_classify<LAYOUT_NARROW, false>) : blocks_per_sm(k_classify<LAYOUT_WIDE, false>);
-        db->classify_blocks_per_sm[variant] = n;
-    }
+    const int variant = (narrow ? 0 : local ? 4 : 2) + (d_rows ? 1 : 0);
+    void (*kern)(const ClassifyParams) =
+        d_rows ? (narrow ? k_classify<LAYOUT_NARROW, true> : local ? k_classify<LAYOUT_LOCAL, true> : k_classify<LAYOUT_WIDE, true>)
+               : (narrow ? k_classify<LAYOUT_NARROW, false> : local ? k_classify<LAYOUT_LOCAL, false> : k_classify<LAYOUT_WIDE, false>);
+    if (!db->classify_blocks_per_sm[variant]) db->classify_blocks_per_sm[variant] = blocks_per_sm(kern);
     const int blocks_needed = (int)((n_reads + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
     const int blocks = std::min(blocks_needed, db->sm_count * db->classify_blocks_per_sm[variant]);
-    if (d_rows) {
-        if (narrow) k_classify<LAYOUT_NARROW, true><<<blocks, WARPS_PER_BLOCK * 32, 0, st>>>(p);
-        else k_classify<LAYOUT_WIDE, true><<<blocks, WARPS_PER_BLOCK * 32, 0, st>>>(p);
-    } else {
-        if (narrow) k_classify<LAYOUT_NARROW, false><<<blocks, WARPS_PER_BLOCK * 32, 0, st>>>(p);
-        else k_classify<LAYOUT_WIDE, false><<<blocks, WARPS_PER_BLOCK * 32, 0, st>>>(p);
-    }
+    kern<<<blocks, WARPS_PER_BLOCK * 32, 0, st>>>(p);
     CK(cudaGetLastError());
     // exact fallback; exits at once when the list is empty. Its histogram
     // scratch is shared, so dense kernels are chained across streams.
     std::lock_guard<std::mutex> dense_guard(db->dense_mu);
     CK(cudaStreamWaitEvent(st, db->dense_chain, 0));
     if (narrow) k_classify_dense<LAYOUT_NARROW><<<db->dense_blocks, 256, 0, st>>>(p, db->d_dense_hist);
+    else if (local) k_classify_dense<LAYOUT_LOCAL><<<db->dense_blocks, 256, 0, st>>>(p, db->d_dense_hist);
     else k_classify_dense<LAYOUT_WIDE><<<db->dense_blocks, 256, 0, st>>>(p, db->d_dense_hist);
     CK(cudaGetLastError());
     CK(cudaEventRecord(db->dense_chain, st));

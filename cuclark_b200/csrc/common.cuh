@@ -18,6 +18,21 @@
 //     word 6      label[0] | label[1] << 16
 //     word 7      label[2] | meta << 16
 //
+//   LOCAL (k >= 19, large tables): the home of a k-mer is chosen by its canonical MINIMIZER
+//     (the m-mer, m = k-7, with the smallest hash among the 8 m-mers of the k-mer; both
+//     strands give the same one), so that the ~4.5 consecutive k-mers of a read that share a
+//     minimizer probe the SAME 128-byte line: line = mix(minimizer) mod NL, sector within the
+//     line = minimizer offset & 3 (consecutive k-mers -> consecutive offsets -> the group is
+//     spread evenly over the 4 sectors of its line). Adjacent lanes of a warp then coalesce
+//     into one line request instead of one random sector each. The slot still identifies the
+//     k-mer exactly: key = mix(minimizer) div NL (<= 19 bit) | the 7 other nucleotides (14 bit)
+//     | offset (3 bit) | strand of the minimizer (1 bit) = 37 bit.
+//     word 0..3   key[0..3] low 32 bits      (all-ones + high byte 0xFF = empty)
+//     word 4      label[0] | label[1] << 16
+//     word 5      label[2] | label[3] << 16
+//     word 6      key high bits, one byte per slot
+//     word 7      meta << 16
+//
 //   meta bit 0 = "overflowed": more k-mers are homed here than the bucket has
 //   slots; the excess lives in the OVERFLOW table, a second, sparsely filled
 //   array of WIDE buckets keyed by the full canonical k-mer, addressed by an
@@ -36,8 +51,15 @@ namespace cuclark {
 
 constexpr int LAYOUT_NARROW = 1;
 constexpr int LAYOUT_WIDE = 2;
+constexpr int LAYOUT_LOCAL = 3;
 constexpr int NARROW_SLOTS = 5;
 constexpr int WIDE_SLOTS = 3;
+constexpr int LOCAL_SLOTS = 4;
+constexpr int LOCAL_W = 8;             // m-mers per k-mer (m = k - LOCAL_W + 1)
+constexpr int LOCAL_ZQ_BITS = 19;      // bits of mix(minimizer) div NL kept in the key
+constexpr int LOCAL_REST_BITS = 2 * (LOCAL_W - 1);
+constexpr int LOCAL_MIN_K = 19;        // m >= 12: the order hash takes the top 24 bits of a >= 24-bit value
+constexpr uint32_t LOCAL_ORDER_MAX = 0xFFFFFEu;    // 24-bit order hash, all-ones reserved for "no m-mer"
 constexpr uint32_t NO_LABEL = 0xFFFFFFFFu;
 constexpr uint64_t OVF_EMPTY = ~0ull;
 constexpr uint64_t OVF_TOMBSTONE = ~0ull - 1;
@@ -51,6 +73,8 @@ struct TableView {
     uint64_t lo;            // this shard holds home buckets [lo, lo+n_local)
     uint64_t n_local;
     uint64_t n_ovf;         // buckets in the overflow table
+    uint64_t NL;            // LOCAL: number of 128-byte lines (M = 4 NL), and floor(2^64 / NL)
+    uint64_t magicNL;
     int layout;
     int k;
 };
@@ -88,6 +112,90 @@ __device__ __forceinline__ void divmod_M(uint64_t c, uint64_t M, uint64_t magic,
     if (r >= M) { r -= M; q++; }
 }
 
+// ---- LOCAL layout: minimizer-addressed lines ---------------------------------------
+// Invertible mixing of an nbits-wide value (24 <= nbits <= 50): xor-shifts by ceil(nbits/2) are
+// involutions, the multiplier is odd, so local_unmix() undoes it exactly.
+constexpr uint64_t LOCAL_MUL = 0xD6E8FEB86659FD93ull;
+
+__host__ __device__ __forceinline__ uint64_t local_mix(uint64_t u, int nbits) {
+    const uint64_t mask = (~0ull) >> (64 - nbits);
+    const int s = (nbits + 1) >> 1;
+    u ^= u >> s;
+    u = (u * LOCAL_MUL) & mask;
+    u ^= u >> s;
+    return u;
+}
+__host__ __device__ __forceinline__ uint64_t inv_odd64(uint64_t a) {   // a * x == 1 mod 2^64
+    uint64_t x = a;
+    for (int i = 0; i < 6; i++) x *= 2 - a * x;
+    return x;
+}
+__host__ __device__ __forceinline__ uint64_t local_unmix(uint64_t z, int nbits) {
+    const uint64_t mask = (~0ull) >> (64 - nbits);
+    const int s = (nbits + 1) >> 1;
+    z ^= z >> s;
+    z = (z * inv_odd64(LOCAL_MUL)) & mask;
+    z ^= z >> s;
+    return z;
+}
+// order of the m-mers inside a k-mer: the top 24 bits of the mixed canonical m-mer
+__host__ __device__ __forceinline__ uint32_t local_order(uint64_t z, int nbits) {
+    const uint32_t h = (uint32_t)(z >> (nbits - 24));
+    return h > LOCAL_ORDER_MAX ? LOCAL_ORDER_MAX : h;
+}
+// canonical m-mer at offset o of the 2k-bit code y (first nucleotide in the high bits);
+// fwd tells whether the form standing in y is the strictly smaller one
+__host__ __device__ __forceinline__ uint64_t local_mmer(uint64_t y, int o, int m, bool& fwd) {
+    const uint64_t a = (y >> (2 * (LOCAL_W - 1 - o))) & ((~0ull) >> (64 - 2 * m));
+    const uint64_t b = revcomp2(a, m);
+    fwd = a < b;
+    return fwd ? a : b;
+}
+// the 2(W-1) bits of c around its m-mer at offset o
+__host__ __device__ __forceinline__ uint32_t local_rest(uint64_t c, int o, int m) {
+    const uint32_t lomask = (1u << (2 * (LOCAL_W - 1 - o))) - 1u;
+    return ((uint32_t)(c >> (2 * m)) & ~lomask) | ((uint32_t)c & lomask);
+}
+// key = zq | rest << 19 | o << 33 | fwd << 36, as its low word and its high byte
+__host__ __device__ __forceinline__ uint32_t local_key_lo(uint64_t zq, uint32_t rest) { return (uint32_t)zq | (rest << LOCAL_ZQ_BITS); }
+__host__ __device__ __forceinline__ uint32_t local_key_hi(uint32_t rest, int o, bool fwd) {
+    return (rest >> (32 - LOCAL_ZQ_BITS)) | ((uint32_t)o << 1) | ((uint32_t)fwd << 4);
+}
+// Home of the canonical k-mer c: its minimizer is the m-mer with the smallest order hash,
+// the LEFTMOST such offset in c's own orientation on ties. Returns the global sector index
+// (line * 4 + (offset & 3)) and the 37-bit key. Reference form: the classify kernel computes
+// the same thing with a rolling window minimum across lanes.
+__host__ __device__ __forceinline__ void local_locate(uint64_t c, int k, uint64_t NL, uint64_t& sector, uint64_t& key) {
+    const int m = k - LOCAL_W + 1;
+    uint32_t best = 0xFFFFFFFFu;
+    int bo = 0;
+    bool bf = true;
+    uint64_t bz = 0;
+    for (int o = 0; o < LOCAL_W; o++) {
+        bool fwd;
+        const uint64_t z = local_mix(local_mmer(c, o, m, fwd), 2 * m);
+        const uint32_t h = local_order(z, 2 * m);
+        if (h < best) { best = h; bo = o; bf = fwd; bz = z; }
+    }
+    const uint64_t line = bz % NL, zq = bz / NL;
+    const uint32_t rest = local_rest(c, bo, m);
+    sector = line * 4 + (uint64_t)(bo & 3);
+    key = (uint64_t)local_key_lo(zq, rest) | ((uint64_t)local_key_hi(rest, bo, bf) << 32);
+}
+// inverse of local_locate: the canonical k-mer stored as `key` in (a sector of) `line`
+__host__ __device__ __forceinline__ uint64_t local_rebuild(uint64_t line, uint64_t key, int k, uint64_t NL) {
+    const int m = k - LOCAL_W + 1;
+    const uint64_t zq = key & ((1ull << LOCAL_ZQ_BITS) - 1);
+    const uint64_t rest = (key >> LOCAL_ZQ_BITS) & ((1ull << LOCAL_REST_BITS) - 1);
+    const int o = (int)((key >> (LOCAL_ZQ_BITS + LOCAL_REST_BITS)) & 7u);
+    const bool fwd = (key >> (LOCAL_ZQ_BITS + LOCAL_REST_BITS + 3)) & 1u;
+    const uint64_t u = local_unmix(zq * NL + line, 2 * m);
+    const uint64_t mm = fwd ? u : revcomp2(u, m);            // !fwd: the larger (or the equal) form stands in c
+    const int lo_bits = 2 * (LOCAL_W - 1 - o);
+    const uint64_t lo = rest & ((1ull << lo_bits) - 1), hi = rest >> lo_bits;
+    return (o ? hi << (2 * m + lo_bits) : 0) | (mm << lo_bits) | lo;
+}
+
 // ---- 32-byte probe ------------------------------------------------------------
 struct Sector { uint32_t w[8]; };
 
@@ -115,6 +223,14 @@ __device__ __forceinline__ uint32_t match_sector(const Sector& s, uint64_t key) 
             const uint32_t lw = s.w[5 + (i >> 1)];
             if (s.w[i] == k32) label = (i & 1) ? (lw >> 16) : (lw & 0xFFFFu);
         }
+    } else if (LAYOUT == LAYOUT_LOCAL) {
+        const uint32_t k32 = (uint32_t)key;
+        const uint32_t eqhi = __vcmpeq4(s.w[6], (uint32_t)(key >> 32) * 0x01010101u);   // 0xFF where the high byte matches
+#pragma unroll
+        for (int i = 0; i < LOCAL_SLOTS; i++) {
+            const uint32_t lw = s.w[4 + (i >> 1)];
+            if (s.w[i] == k32 && ((eqhi >> (8 * i)) & 1u)) label = (i & 1) ? (lw >> 16) : (lw & 0xFFFFu);
+        }
     } else {
 #pragma unroll
         for (int i = 0; i < WIDE_SLOTS; i++) {
@@ -124,6 +240,17 @@ __device__ __forceinline__ uint32_t match_sector(const Sector& s, uint64_t key) 
         }
     }
     return label;
+}
+
+// LOCAL probes: the whole 128-byte line is wanted in L2 (the neighbouring lanes / the next
+// round read its other sectors)
+__device__ __forceinline__ Sector load_sector_line(const uint4* p) {
+    Sector s;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(s.w[0]), "=r"(s.w[1]), "=r"(s.w[2]), "=r"(s.w[3]),
+                   "=r"(s.w[4]), "=r"(s.w[5]), "=r"(s.w[6]), "=r"(s.w[7])
+                 : "l"(p));
+    return s;
 }
 
 __device__ __forceinline__ bool sector_overflowed(const Sector& s) { return (s.w[7] >> 16) & 1u; }
@@ -136,7 +263,18 @@ __host__ __device__ __forceinline__ uint64_t ovf_home(uint64_t c, uint64_t n_ovf
 #endif
 }
 
-// Overflow table: linear probing over WIDE buckets holding the full k-mer.
+// Overflow table: linear probing over WIDE buckets holding the full k-mer, from bucket b on
+// (n0 buckets of the sequence have been looked at already).
+__device__ __forceinline__ uint32_t ovf_lookup_from(const TableView& t, uint64_t c, uint64_t b, uint64_t n0) {
+    for (uint64_t n = n0; n < t.n_ovf; n++) {
+        const Sector s = load_sector(t.ovf + 2 * b);
+        const uint32_t label = match_sector<LAYOUT_WIDE>(s, c);
+        if (label != NO_LABEL) return label;
+        if (((uint64_t)s.w[4] | ((uint64_t)s.w[5] << 32)) == OVF_EMPTY) return NO_LABEL;
+        if (++b == t.n_ovf) b = 0;
+    }
+    return NO_LABEL;
+}
 __device__ __forceinline__ uint32_t ovf_lookup(const TableView& t, uint64_t c) {
     uint64_t b = ovf_home(c, t.n_ovf);
     for (uint64_t n = 0; n < t.n_ovf; n++) {
@@ -155,7 +293,8 @@ __device__ __forceinline__ uint32_t ovf_lookup(const TableView& t, uint64_t c) {
 template <int LAYOUT>
 __device__ __forceinline__ uint32_t table_lookup(const TableView& t, uint64_t c) {
     uint64_t q, b;
-    divmod_M(c, t.M, t.magic, q, b);
+    if (LAYOUT == LAYOUT_LOCAL) local_locate(c, t.k, t.NL, b, q);
+    else divmod_M(c, t.M, t.magic, q, b);
     const uint64_t lb = b - t.lo;
     if (lb >= t.n_local) return NO_LABEL;           // other shard (b < lo wraps around)
     const Sector s = load_sector(t.buckets + 2 * lb);

@@ -61,7 +61,7 @@ struct cuclark_db {
     cudaEvent_t dense_chain = nullptr; //   serialised across streams through this event
     std::mutex dense_mu;               //   (wait + launch + record must not interleave between host threads)
     int dense_blocks = 0;
-    int classify_blocks_per_sm[4] = {0, 0, 0, 0};
+    int classify_blocks_per_sm[6] = {0, 0, 0, 0, 0, 0};
     int sm_count = 0;
     cudaStream_t stream = nullptr;     // library-owned default stream
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;

@@ -30,6 +30,7 @@ namespace {
 
 constexpr uint32_t ERR_OVF_LIST = 1, ERR_COUNTER = 2, ERR_NO_SLOT = 4;
 constexpr double OVF_LOAD = 0.75;                  // mean entries per 3-slot overflow bucket
+constexpr double OVF_LOAD_LOCAL = 1.2;             // LOCAL spills ~13% of the entries: a denser overflow table
 constexpr int CHUNK_THREADS = 1024;
 constexpr uint32_t CHUNK_BLOCKS = 8192;            // 8.4M reference buckets per chunk
 
@@ -45,7 +46,20 @@ struct BuildCtx {
     uint4* ovf;            // overflow table (allocated after phase 1)
     uint32_t* ovf_cnt8;
     uint64_t n_ovf;
+    uint64_t NL;           // LOCAL: lines (M = 4 NL)
+    int k, layout;
 };
+
+// global home bucket b and in-bucket key q of the canonical k-mer c
+template <int LAYOUT>
+__device__ __forceinline__ void home_of(uint64_t c, uint64_t M, uint64_t magic, uint64_t NL, int k, uint64_t& q, uint64_t& b) {
+    if (LAYOUT == LAYOUT_LOCAL) local_locate(c, k, NL, b, q);
+    else divmod_M(c, M, magic, q, b);
+}
+__device__ __forceinline__ void home_of_rt(int layout, uint64_t c, uint64_t M, uint64_t magic, uint64_t NL, int k, uint64_t& q, uint64_t& b) {
+    if (layout == LAYOUT_LOCAL) local_locate(c, k, NL, b, q);
+    else divmod_M(c, M, magic, q, b);
+}
 
 template <int LAYOUT>
 __device__ __forceinline__ void write_slot(uint4* table, uint64_t lb, uint32_t slot, uint64_t q, uint32_t label) {
@@ -53,6 +67,10 @@ __device__ __forceinline__ void write_slot(uint4* table, uint64_t lb, uint32_t s
     if (LAYOUT == LAYOUT_NARROW) {
         w[slot] = (uint32_t)q;
         atomicOr(&w[5 + (slot >> 1)], label << (16 * (slot & 1)));
+    } else if (LAYOUT == LAYOUT_LOCAL) {
+        w[slot] = (uint32_t)q;
+        atomicOr(&w[4 + (slot >> 1)], label << (16 * (slot & 1)));
+        atomicAnd(&w[6], ~(0xFFu << (8 * slot)) | ((uint32_t)(q >> 32) << (8 * slot)));   // byte was 0xFF
     } else {
         reinterpret_cast<uint64_t*>(w)[slot] = q;
         atomicOr(&w[6 + (slot >> 1)], label << (16 * (slot & 1)));
@@ -68,9 +86,9 @@ __device__ __forceinline__ uint32_t claim_slot(uint32_t* cnt8, uint32_t* flags, 
 
 template <int LAYOUT>
 __device__ __forceinline__ bool insert_home(const BuildCtx& x, uint64_t c, uint32_t label) {
-    constexpr uint32_t SLOTS = LAYOUT == LAYOUT_NARROW ? NARROW_SLOTS : WIDE_SLOTS;
+    constexpr uint32_t SLOTS = LAYOUT == LAYOUT_NARROW ? NARROW_SLOTS : LAYOUT == LAYOUT_LOCAL ? LOCAL_SLOTS : WIDE_SLOTS;
     uint64_t q, b;
-    divmod_M(c, x.M, x.magic, q, b);
+    home_of<LAYOUT>(c, x.M, x.magic, x.NL, x.k, q, b);
     const uint64_t lb = b - x.lo;
     if (lb >= x.n_local) return false;               // homed in another shard
     const uint32_t slot = claim_slot(x.cnt8, x.flags, lb);
@@ -90,6 +108,8 @@ __global__ void k_init_table(uint4* table, uint64_t n_local, int layout) {
     uint4 v;
     if (layout == LAYOUT_NARROW) {
         v = (i & 1) ? make_uint4(0xFFFFFFFFu, 0u, 0u, 0u) : make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+    } else if (layout == LAYOUT_LOCAL) {
+        v = (i & 1) ? make_uint4(0u, 0u, 0xFFFFFFFFu, 0u) : make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
     } else {
         v = (i & 1) ? make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u) : make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
     }
@@ -148,7 +168,7 @@ __global__ void k_place_spills(BuildCtx x, uint32_t n) {
     const uint64_t c = x.ovf_c[i];
     const uint32_t label = x.ovf_l[i];
     uint64_t q, b;
-    divmod_M(c, x.M, x.magic, q, b);
+    home_of_rt(x.layout, c, x.M, x.magic, x.NL, x.k, q, b);
     const uint64_t lb = b - x.lo;
     atomicOr(reinterpret_cast<uint32_t*>(x.table + 2 * lb) + 7, 1u << 16);
     uint64_t ob = ovf_home(c, x.n_ovf);
@@ -217,7 +237,32 @@ template <int LAYOUT>
 struct DedupeView {
     uint4* table; uint4* ovf; uint64_t M, lo, n_local, n_ovf;
     uint8_t* del_main; uint8_t* del_ovf;
+    uint64_t NL; int k;
 };
+
+template <int LAYOUT> struct SlotsOf { static constexpr int n = LAYOUT == LAYOUT_NARROW ? NARROW_SLOTS : LAYOUT == LAYOUT_LOCAL ? LOCAL_SLOTS : WIDE_SLOTS; };
+
+// key, label and occupancy of slot s of a home bucket
+template <int LAYOUT>
+__device__ __forceinline__ bool read_slot(const uint32_t* w, int s, uint64_t& key, uint32_t& label) {
+    if (LAYOUT == LAYOUT_NARROW) {
+        key = w[s];
+        const uint32_t lw = w[5 + (s >> 1)];
+        label = (s & 1) ? (lw >> 16) : (lw & 0xFFFFu);
+        return w[s] != 0xFFFFFFFFu;
+    } else if (LAYOUT == LAYOUT_LOCAL) {
+        const uint32_t hi = (w[6] >> (8 * s)) & 0xFFu;
+        key = (uint64_t)w[s] | ((uint64_t)hi << 32);
+        const uint32_t lw = w[4 + (s >> 1)];
+        label = (s & 1) ? (lw >> 16) : (lw & 0xFFFFu);
+        return hi != 0xFFu;
+    } else {
+        key = reinterpret_cast<const uint64_t*>(w)[s];
+        const uint32_t lw = w[6 + (s >> 1)];
+        label = (s & 1) ? (lw >> 16) : (lw & 0xFFFFu);
+        return key != OVF_EMPTY;
+    }
+}
 
 __device__ __forceinline__ uint64_t wide_key(const uint32_t* w, int s) { return reinterpret_cast<const uint64_t*>(w)[s]; }
 __device__ __forceinline__ uint32_t wide_label(const uint32_t* w, int s) { const uint32_t lw = w[6 + (s >> 1)]; return (s & 1) ? (lw >> 16) : (lw & 0xFFFFu); }
@@ -248,7 +293,7 @@ __device__ __forceinline__ uint32_t ovf_scan(const uint4* ovf, uint64_t n_ovf, u
 
 template <int LAYOUT>
 __global__ void k_dedupe_main(DedupeView<LAYOUT> v) {
-    constexpr int SLOTS = LAYOUT == LAYOUT_NARROW ? NARROW_SLOTS : WIDE_SLOTS;
+    constexpr int SLOTS = SlotsOf<LAYOUT>::n;
     const uint64_t lb = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (lb >= v.n_local) return;
     const uint32_t* w = reinterpret_cast<const uint32_t*>(v.table + 2 * lb);
@@ -256,16 +301,7 @@ __global__ void k_dedupe_main(DedupeView<LAYOUT> v) {
     uint64_t keys[SLOTS];
     uint32_t labels[SLOTS];
     bool used[SLOTS];
-    for (int s = 0; s < SLOTS; s++) {
-        if (LAYOUT == LAYOUT_NARROW) {
-            keys[s] = w[s]; used[s] = w[s] != 0xFFFFFFFFu;
-            const uint32_t lw = w[5 + (s >> 1)];
-            labels[s] = (s & 1) ? (lw >> 16) : (lw & 0xFFFFu);
-        } else {
-            keys[s] = wide_key(w, s); used[s] = keys[s] != OVF_EMPTY;
-            labels[s] = wide_label(w, s);
-        }
-    }
+    for (int s = 0; s < SLOTS; s++) used[s] = read_slot<LAYOUT>(w, s, keys[s], labels[s]);
     uint32_t del = 0;
     for (int i = 0; i < SLOTS; i++) {
         if (!used[i]) continue;
@@ -277,7 +313,8 @@ __global__ void k_dedupe_main(DedupeView<LAYOUT> v) {
         }
         if (flagged && v.n_ovf) {
             uint32_t total;
-            ovf_scan(v.ovf, v.n_ovf, keys[i] * v.M + (lb + v.lo), labels[i], ~0ull, 0, differ, total);
+            const uint64_t c = LAYOUT == LAYOUT_LOCAL ? local_rebuild((lb + v.lo) >> 2, keys[i], v.k, v.NL) : keys[i] * v.M + (lb + v.lo);
+            ovf_scan(v.ovf, v.n_ovf, c, labels[i], ~0ull, 0, differ, total);
         }
         if (differ || earlier) del |= 1u << i;      // main copies precede overflow copies
     }
@@ -286,7 +323,7 @@ __global__ void k_dedupe_main(DedupeView<LAYOUT> v) {
 
 template <int LAYOUT>
 __global__ void k_dedupe_ovf(DedupeView<LAYOUT> v, uint64_t magic) {
-    constexpr int SLOTS = LAYOUT == LAYOUT_NARROW ? NARROW_SLOTS : WIDE_SLOTS;
+    constexpr int SLOTS = SlotsOf<LAYOUT>::n;
     const uint64_t ob = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (ob >= v.n_ovf) return;
     const uint32_t* w = reinterpret_cast<const uint32_t*>(v.ovf + 2 * ob);
@@ -300,21 +337,12 @@ __global__ void k_dedupe_ovf(DedupeView<LAYOUT> v, uint64_t magic) {
         const uint32_t before = ovf_scan(v.ovf, v.n_ovf, c, label, ob, s, differ, total);
         // copies in the home bucket
         uint64_t q, b;
-        divmod_M(c, v.M, magic, q, b);
+        home_of<LAYOUT>(c, v.M, magic, v.NL, v.k, q, b);
         const uint32_t* hw = reinterpret_cast<const uint32_t*>(v.table + 2 * (b - v.lo));
         bool in_main = false;
         for (int j = 0; j < SLOTS; j++) {
             uint64_t kk; uint32_t ll;
-            if (LAYOUT == LAYOUT_NARROW) {
-                if (hw[j] == 0xFFFFFFFFu) continue;
-                kk = hw[j];
-                const uint32_t lw = hw[5 + (j >> 1)];
-                ll = (j & 1) ? (lw >> 16) : (lw & 0xFFFFu);
-            } else {
-                kk = wide_key(hw, j);
-                if (kk == OVF_EMPTY) continue;
-                ll = wide_label(hw, j);
-            }
+            if (!read_slot<LAYOUT>(hw, j, kk, ll)) continue;
             if (kk != q) continue;
             in_main = true;
             if (ll != label) differ = true;
@@ -331,9 +359,10 @@ __global__ void k_dedupe_apply(DedupeView<LAYOUT> v, unsigned long long* removed
     if (i < v.n_local && v.del_main[i]) {
         uint32_t* w = reinterpret_cast<uint32_t*>(v.table + 2 * i);
         const uint32_t del = v.del_main[i];
-        for (int s = 0; s < (LAYOUT == LAYOUT_NARROW ? NARROW_SLOTS : WIDE_SLOTS); s++) {
+        for (int s = 0; s < SlotsOf<LAYOUT>::n; s++) {
             if (!((del >> s) & 1u)) continue;
             if (LAYOUT == LAYOUT_NARROW) w[s] = 0xFFFFFFFFu;
+            else if (LAYOUT == LAYOUT_LOCAL) { w[s] = 0xFFFFFFFFu; w[6] |= 0xFFu << (8 * s); }
             else reinterpret_cast<uint64_t*>(w)[s] = OVF_EMPTY;
             gone++;
         }
@@ -354,11 +383,18 @@ __global__ void k_dedupe_apply(DedupeView<LAYOUT> v, unsigned long long* removed
 struct Geometry {
     int layout;
     uint64_t M, lo, n_local;
+    uint64_t NL;            // LOCAL: lines; M = 4 NL
 };
+
+// LOCAL needs mix(minimizer) div NL to fit LOCAL_ZQ_BITS: NL >= 4^m / 2^19 (m = k - 7)
+uint64_t local_min_lines(int k) {
+    const int mbits = 2 * (k - LOCAL_W + 1);
+    return mbits > LOCAL_ZQ_BITS ? (1ull << (mbits - LOCAL_ZQ_BITS)) : 1;
+}
 
 uint64_t pow4(int k) { return k >= 32 ? 0 : (1ull << (2 * k)); }   // 0 means 2^64
 
-Geometry choose_geometry(const cuclark_config& cfg, uint64_t n_entries, double grow) {
+Geometry choose_geometry(const cuclark_config& cfg, uint64_t n_entries, double grow, bool allow_auto_local = true) {
     Geometry g;
     const double narrow_load = cfg.bucket_load > 0 ? cfg.bucket_load : 2.6;
     const double wide_load = cfg.bucket_load > 0 ? std::min(cfg.bucket_load, 2.0) : 1.5;
@@ -369,6 +405,34 @@ Geometry choose_geometry(const cuclark_config& cfg, uint64_t n_entries, double g
     uint64_t m_narrow = (uint64_t)((double)n_entries / narrow_load * grow) + 64;
     uint64_t m_wide = (uint64_t)((double)n_entries / wide_load * grow) + 64;
     int layout = cfg.layout;
+    // LOCAL needs at least local_min_lines(k) lines (key width); a table that would be mostly
+    // empty at that size (small database at large k) uses the hashed layouts instead
+    // (and enough distinct minimizers: about 1 in 9 canonical m-mers ever is one)
+    const double local_load = cfg.bucket_load > 0 ? std::min(cfg.bucket_load, 3.5) : 2.5;
+    const double local_lines = (double)n_entries / (4.0 * local_load) * grow + 16;
+    const bool local_fits = cfg.k >= LOCAL_MIN_K && cfg.k <= 32 &&
+        (local_min_lines(cfg.k) * 128ull <= (8ull << 30) || (double)local_min_lines(cfg.k) <= 4.0 * local_lines) &&
+        (double)pow4(cfg.k - LOCAL_W + 1) / 9.0 >= 4.0 * local_lines;
+    // automatic choice: minimizer lines for a single-device table that fills them (at bacterial scale they
+    // serve ~1.25x the lookups of the hashed sectors; a small database would pay the minimum size for nothing)
+    if (layout == 0 && allow_auto_local && cfg.shard_count <= 1 && local_fits && cfg.bucket_load <= 0 &&
+        (double)local_min_lines(cfg.k) <= 1.25 * local_lines && !getenv("CUCLARK_NO_LOCAL"))
+        layout = LAYOUT_LOCAL;
+    if (layout == LAYOUT_LOCAL && local_fits) {
+        // entries per 4-slot sector; the k-mers of a read that share a minimizer arrive in
+        // clumps of ~4.5 per line, so the load stays below that of the hashed layouts
+        uint64_t nl = (uint64_t)local_lines;
+        nl = std::max(nl, local_min_lines(cfg.k)) | 1ull;
+        g.layout = LAYOUT_LOCAL;
+        g.NL = nl;
+        g.M = 4 * nl;
+        const uint64_t G = cfg.shard_count > 1 ? cfg.shard_count : 1, i = cfg.shard_count > 1 ? cfg.shard_index : 0;
+        g.lo = 4 * (uint64_t)((__uint128_t)nl * i / G);          // shards hold whole lines
+        g.n_local = 4 * (uint64_t)((__uint128_t)nl * (i + 1) / G) - g.lo;
+        return g;
+    }
+    if (layout == LAYOUT_LOCAL) layout = 0;                      // k too small / table too small for minimizer lines
+    g.NL = 0;
     if (layout == 0) {
         if (!narrow_possible) layout = LAYOUT_WIDE;
         else {
@@ -408,11 +472,12 @@ struct BuildBuffers {
     void free_all() { free_temp(); cudaFree(table); cudaFree(ovf); table = nullptr; ovf = nullptr; }
 };
 
-int alloc_build(const Geometry& g, uint64_t n_expected, BuildBuffers& b, BuildCtx& x, uint64_t htsize) {
+int alloc_build(const Geometry& g, uint64_t n_expected, BuildBuffers& b, BuildCtx& x, uint64_t htsize, int k) {
+    x.k = k;
     if (g.n_local >= 0xFFFFFFFFull) { set_error("shard of %llu buckets exceeds 2^32: use more shards", (unsigned long long)g.n_local); return CUCLARK_ERR_ARG; }
     const uint64_t G = 1;
     (void)G;
-    uint64_t ovf_cap64 = n_expected / 6 + (1u << 16);
+    uint64_t ovf_cap64 = (g.layout == LAYOUT_LOCAL ? n_expected / 3 : n_expected / 6) + (1u << 16);
     if (ovf_cap64 > 0xFFFFFF00ull) ovf_cap64 = 0xFFFFFF00ull;
     if (cudaMalloc(&b.table, g.n_local * 32) != cudaSuccess) { cudaGetLastError(); set_error("cudaMalloc of %.2f GB table failed", g.n_local * 32 / 1e9); return CUCLARK_ERR_NOMEM; }
     CK(cudaMalloc(&b.cnt8, (g.n_local / 4 + 1) * 4));
@@ -428,6 +493,7 @@ int alloc_build(const Geometry& g, uint64_t n_expected, BuildBuffers& b, BuildCt
     CK(cudaGetLastError());
     x.table = b.table; x.cnt8 = b.cnt8; x.M = g.M; x.magic = (uint64_t)((((__uint128_t)1) << 64) / g.M);
     x.lo = g.lo; x.n_local = g.n_local; x.htsize = htsize;
+    x.NL = g.NL; x.layout = g.layout;
     x.ovf_c = b.ovf_c; x.ovf_l = b.ovf_l; x.ovf_cap = (uint32_t)ovf_cap64; x.flags = b.flags;
     x.inserted = b.counters;
     return CUCLARK_OK;
@@ -441,7 +507,7 @@ int finish_build(cuclark_db* db, const Geometry& g, BuildBuffers& b, BuildCtx& x
     const uint32_t n_ovf_entries = flags[0];
     uint64_t n_ovf = 0;
     if (n_ovf_entries) {
-        n_ovf = (uint64_t)((double)n_ovf_entries / OVF_LOAD) + 64;
+        n_ovf = (uint64_t)((double)n_ovf_entries / (g.layout == LAYOUT_LOCAL ? OVF_LOAD_LOCAL : OVF_LOAD)) + 64;
         if (cudaMalloc(&b.ovf, n_ovf * 32) != cudaSuccess) { cudaGetLastError(); set_error("cudaMalloc of overflow table failed"); return CUCLARK_ERR_NOMEM; }
         CK(cudaMalloc(&b.ovf_cnt8, (n_ovf / 4 + 1) * 4));
         CK(cudaMemset(b.ovf_cnt8, 0, (n_ovf / 4 + 1) * 4));
@@ -456,13 +522,19 @@ int finish_build(cuclark_db* db, const Geometry& g, BuildBuffers& b, BuildCtx& x
         CK(cudaMalloc(&b.del_ovf, n_ovf + 1));
         const unsigned blocks = (unsigned)((std::max(g.n_local, n_ovf) + 255) / 256);
         if (g.layout == LAYOUT_NARROW) {
-            DedupeView<LAYOUT_NARROW> v{b.table, b.ovf, g.M, g.lo, g.n_local, n_ovf, b.del_main, b.del_ovf};
+            DedupeView<LAYOUT_NARROW> v{b.table, b.ovf, g.M, g.lo, g.n_local, n_ovf, b.del_main, b.del_ovf, g.NL, x.k};
             k_dedupe_main<LAYOUT_NARROW><<<(unsigned)((g.n_local + 255) / 256), 256>>>(v);
             if (n_ovf) k_dedupe_ovf<LAYOUT_NARROW><<<(unsigned)((n_ovf + 255) / 256), 256>>>(v, x.magic);
             else CK(cudaMemset(b.del_ovf, 0, 1));
             k_dedupe_apply<LAYOUT_NARROW><<<blocks, 256>>>(v, b.counters + 2);
+        } else if (g.layout == LAYOUT_LOCAL) {
+            DedupeView<LAYOUT_LOCAL> v{b.table, b.ovf, g.M, g.lo, g.n_local, n_ovf, b.del_main, b.del_ovf, g.NL, x.k};
+            k_dedupe_main<LAYOUT_LOCAL><<<(unsigned)((g.n_local + 255) / 256), 256>>>(v);
+            if (n_ovf) k_dedupe_ovf<LAYOUT_LOCAL><<<(unsigned)((n_ovf + 255) / 256), 256>>>(v, x.magic);
+            else CK(cudaMemset(b.del_ovf, 0, 1));
+            k_dedupe_apply<LAYOUT_LOCAL><<<blocks, 256>>>(v, b.counters + 2);
         } else {
-            DedupeView<LAYOUT_WIDE> v{b.table, b.ovf, g.M, g.lo, g.n_local, n_ovf, b.del_main, b.del_ovf};
+            DedupeView<LAYOUT_WIDE> v{b.table, b.ovf, g.M, g.lo, g.n_local, n_ovf, b.del_main, b.del_ovf, g.NL, x.k};
             k_dedupe_main<LAYOUT_WIDE><<<(unsigned)((g.n_local + 255) / 256), 256>>>(v);
             if (n_ovf) k_dedupe_ovf<LAYOUT_WIDE><<<(unsigned)((n_ovf + 255) / 256), 256>>>(v, x.magic);
             else CK(cudaMemset(b.del_ovf, 0, 1));
@@ -491,6 +563,8 @@ int finish_build(cuclark_db* db, const Geometry& g, BuildBuffers& b, BuildCtx& x
     db->view.n_local = g.n_local;
     db->view.layout = g.layout;
     db->view.k = db->cfg.k;
+    db->view.NL = g.NL;
+    db->view.magicNL = g.NL ? (uint64_t)((((__uint128_t)1) << 64) / g.NL) : 0;
     b.free_temp();
     return CUCLARK_OK;
 }
@@ -652,12 +726,17 @@ int table_build_from_arrays(cuclark_db* db, const uint8_t* sz_in, const void* ky
 
     int rc = CUCLARK_ERR_BUILD;
     double grow = 1.0;
-    for (int attempt = 0; attempt < 4 && rc == CUCLARK_ERR_BUILD; attempt++, grow *= 1.3) {
-        const Geometry g = choose_geometry(db->cfg, kept, grow);
+    bool auto_local = true, grow_next = false;   // an automatically chosen LOCAL table falls back to the hashed layouts if it cannot be built
+    for (int attempt = 0; attempt < 6 && rc == CUCLARK_ERR_BUILD; attempt++) {
+        if (grow_next) grow *= 1.3;
+        const Geometry g = choose_geometry(db->cfg, kept, grow, auto_local);
+        const bool is_auto_local = db->cfg.layout == 0 && g.layout == LAYOUT_LOCAL;
+        grow_next = !is_auto_local;
+        if (is_auto_local) auto_local = false;
         BuildBuffers bb;
         BuildCtx x{};
-        rc = alloc_build(g, kept / (db->cfg.shard_count > 1 ? db->cfg.shard_count : 1), bb, x, H);
-        if (rc != CUCLARK_OK) { bb.free_all(); break; }
+        rc = alloc_build(g, kept / (db->cfg.shard_count > 1 ? db->cfg.shard_count : 1), bb, x, H, db->cfg.k);
+        if (rc != CUCLARK_OK) { bb.free_all(); if (is_auto_local && rc == CUCLARK_ERR_NOMEM) { rc = CUCLARK_ERR_BUILD; continue; } break; }
         if (cudaDeviceSynchronize() != cudaSuccess) {              // the table is initialised on the default stream
             set_error("table initialisation failed: %s", cudaGetErrorString(cudaGetLastError()));
             bb.free_all();
@@ -694,6 +773,8 @@ int table_build_from_arrays(cuclark_db* db, const uint8_t* sz_in, const void* ky
             const unsigned blocks = (unsigned)(b1 - b0);
             if (g.layout == LAYOUT_NARROW)
                 k_insert_chunk<LAYOUT_NARROW><<<blocks, CHUNK_THREADS, 0, S.st>>>(x, S.d_sz, S.d_keep, S.d_rel, r0, (uint32_t)(r1 - r0), S.d_keys, S.d_labels, kb);
+            else if (g.layout == LAYOUT_LOCAL)
+                k_insert_chunk<LAYOUT_LOCAL><<<blocks, CHUNK_THREADS, 0, S.st>>>(x, S.d_sz, S.d_keep, S.d_rel, r0, (uint32_t)(r1 - r0), S.d_keys, S.d_labels, kb);
             else
                 k_insert_chunk<LAYOUT_WIDE><<<blocks, CHUNK_THREADS, 0, S.st>>>(x, S.d_sz, S.d_keep, S.d_rel, r0, (uint32_t)(r1 - r0), S.d_keys, S.d_labels, kb);
             e = cudaGetLastError();
@@ -730,22 +811,29 @@ int table_build_synthetic(cuclark_db* db, uint32_t seed, uint32_t n_targets, uin
     expected = per_target * n_targets;
     int rc = CUCLARK_ERR_BUILD;
     double grow = 1.0;
-    for (int attempt = 0; attempt < 4 && rc == CUCLARK_ERR_BUILD; attempt++, grow *= 1.3) {
-        const Geometry g = choose_geometry(db->cfg, expected, grow);
+    bool auto_local = true, grow_next = false;
+    for (int attempt = 0; attempt < 6 && rc == CUCLARK_ERR_BUILD; attempt++) {
+        if (grow_next) grow *= 1.3;
+        const Geometry g = choose_geometry(db->cfg, expected, grow, auto_local);
+        const bool is_auto_local = db->cfg.layout == 0 && g.layout == LAYOUT_LOCAL;
+        grow_next = !is_auto_local;
+        if (is_auto_local) auto_local = false;
         BuildBuffers bb;
         BuildCtx x{};
-        rc = alloc_build(g, expected / (db->cfg.shard_count > 1 ? db->cfg.shard_count : 1), bb, x, db->cfg.htsize);
-        if (rc != CUCLARK_OK) { bb.free_all(); break; }
+        rc = alloc_build(g, expected / (db->cfg.shard_count > 1 ? db->cfg.shard_count : 1), bb, x, db->cfg.htsize, db->cfg.k);
+        if (rc != CUCLARK_OK) { bb.free_all(); if (is_auto_local && rc == CUCLARK_ERR_NOMEM) { rc = CUCLARK_ERR_BUILD; continue; } break; }
         if (light_gap > 0) {
             const uint64_t n = per_target * n_targets;
             const unsigned blocks = (unsigned)((n + 255) / 256);
             if (g.layout == LAYOUT_NARROW) k_synth_insert_light<LAYOUT_NARROW><<<blocks, 256>>>(x, seed, n_targets, genome_len, k, light_gap, per_target);
+            else if (g.layout == LAYOUT_LOCAL) k_synth_insert_light<LAYOUT_LOCAL><<<blocks, 256>>>(x, seed, n_targets, genome_len, k, light_gap, per_target);
             else k_synth_insert_light<LAYOUT_WIDE><<<blocks, 256>>>(x, seed, n_targets, genome_len, k, light_gap, per_target);
         } else {
             const uint64_t runs = (per_target + 63) / 64;
             const uint64_t n = runs * n_targets;
             const unsigned blocks = (unsigned)((n + 127) / 128);
             if (g.layout == LAYOUT_NARROW) k_synth_insert_full<LAYOUT_NARROW><<<blocks, 128>>>(x, seed, n_targets, genome_len, k, runs);
+            else if (g.layout == LAYOUT_LOCAL) k_synth_insert_full<LAYOUT_LOCAL><<<blocks, 128>>>(x, seed, n_targets, genome_len, k, runs);
             else k_synth_insert_full<LAYOUT_WIDE><<<blocks, 128>>>(x, seed, n_targets, genome_len, k, runs);
         }
         cudaError_t e = cudaGetLastError();
@@ -909,8 +997,9 @@ int table_load(cuclark_db* db, const char* path, const char* src_base, int sfact
                   (unsigned long long)h.htsize, h.n_targets, h.shard_index, h.shard_count, h.sfactor, h.layout);
         return CUCLARK_ERR_FORMAT;
     }
-    if ((h.layout != LAYOUT_NARROW && h.layout != LAYOUT_WIDE) || h.M == 0 || h.n_local == 0 || h.n_local >= 0xFFFFFFFFull ||
-        h.lo + h.n_local > h.M || (h.layout == LAYOUT_NARROW && (h.k >= 32 || pow4((int)h.k) / h.M >= 0xFFFFFFFFull))) {
+    if ((h.layout != LAYOUT_NARROW && h.layout != LAYOUT_WIDE && h.layout != LAYOUT_LOCAL) || h.M == 0 || h.n_local == 0 || h.n_local >= 0xFFFFFFFFull ||
+        h.lo + h.n_local > h.M || (h.layout == LAYOUT_NARROW && (h.k >= 32 || pow4((int)h.k) / h.M >= 0xFFFFFFFFull)) ||
+        (h.layout == LAYOUT_LOCAL && ((h.M & 3) || (h.lo & 3) || (h.n_local & 3) || (int)h.k < LOCAL_MIN_K || h.M / 4 < local_min_lines((int)h.k)))) {
         set_error("%s: inconsistent geometry", path); return CUCLARK_ERR_FORMAT;
     }
     if (src_base) {
@@ -942,6 +1031,7 @@ int table_load(cuclark_db* db, const char* path, const char* src_base, int sfact
     db->view.M = h.M; db->view.magic = (uint64_t)((((__uint128_t)1) << 64) / h.M);
     db->view.lo = h.lo; db->view.n_local = h.n_local; db->view.n_ovf = h.n_ovf;
     db->view.layout = (int)h.layout; db->view.k = db->cfg.k;
+    if (h.layout == LAYOUT_LOCAL) { db->view.NL = h.M / 4; db->view.magicNL = (uint64_t)((((__uint128_t)1) << 64) / db->view.NL); }
     db->n_entries = h.n_entries; db->n_spilled = h.n_spilled; db->n_spill_buckets = h.n_spill_buckets;
     db->src_sfactor = (int)h.sfactor;
     for (int i = 0; i < 3; i++) db->src_bytes[i] = h.src_bytes[i];

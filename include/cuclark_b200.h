@@ -66,7 +66,10 @@ typedef struct cuclark_config {
     int shard_index;      /* table-partitioned mode: this handle holds shard i of n          */
     int shard_count;      /*   (contiguous ranges of device buckets); 1 = whole table        */
     double bucket_load;   /* mean entries per 32-byte bucket; 0 = default                    */
-    int layout;           /* 0 auto, 1 narrow (5 x 32-bit key), 2 wide (3 x 64-bit key)      */
+    int layout;           /* 0 auto, 1 narrow (5 x 32-bit key), 2 wide (3 x 64-bit key),     */
+                          /* 3 local (minimizer-addressed 128-byte lines of 4 x 4 37-bit     */
+                          /* keys; k >= 19 and a table of at least 4^(k-7)/2^19 lines; auto  */
+                          /* takes it for single-device tables that fill that minimum)       */
 } cuclark_config;
 
 typedef struct cuclark_stats {
@@ -76,7 +79,7 @@ typedef struct cuclark_stats {
     uint64_t table_bytes;      /* device bytes of this shard's table                         */
     uint64_t n_spilled;        /* entries stored outside their home bucket                   */
     uint64_t n_spill_buckets;  /* buckets with maxdisp > 0                                   */
-    int layout;                /* 1 narrow, 2 wide                                           */
+    int layout;                /* 1 narrow, 2 wide, 3 local                                  */
     int k;
     uint64_t lookups;          /* k-mers looked up by the last classify call                 */
     uint64_t dense_reads;      /* reads of the last call that took the dense fallback        */

@@ -293,6 +293,7 @@ def test_table_partitioned_merge(oracle, light_small):
     parts = torch.zeros((G, n, 2 * c.maxhits + 2), dtype=torch.int16, device="cuda")
     d_ptr = torch.from_numpy(ptr.astype(np.int32)).cuda()
     d_cont = torch.from_numpy(cont.astype(np.int16)).cuda()
+    torch.cuda.synchronize()          # the library works on its own stream: finish torch's fills first
     entries = 0
     shards = []
     for s in range(G):
@@ -306,6 +307,7 @@ def test_table_partitioned_merge(oracle, light_small):
     torch.cuda.synchronize()
     out_rows = torch.zeros((n, 2 * c.maxhits + 2), dtype=torch.int16, device="cuda")
     out_final = torch.zeros((n, 5), dtype=torch.int16, device="cuda")
+    torch.cuda.synchronize()
     shards[0].merge_rows_device(parts.data_ptr(), G, n, out_rows.data_ptr(), out_final.data_ptr())
     shards[0].stats(sync=True)
     torch.cuda.synchronize()
@@ -343,6 +345,7 @@ def test_synthetic_device_generators_match_numpy(oracle):
             per = 1 + (L + 7) // 8
             d_ptr = torch.zeros(n + 1, dtype=torch.int32, device="cuda")
             d_cont = torch.zeros(n * per, dtype=torch.int16, device="cuda")
+            torch.cuda.synchronize()      # the library works on its own stream: finish torch's fills first
             g.synth_reads_device(rseed, seed, T, G, 0, n, L, 10, 100, d_ptr.data_ptr(), d_cont.data_ptr())
             g.stats(sync=True)
             torch.cuda.synchronize()
