@@ -53,10 +53,14 @@ def parse():
     ap.add_argument("--targets", type=int, default=int(os.environ.get("CUCLARK_BENCH_TARGETS", 1430)))
     ap.add_argument("--reads", type=int, default=int(os.environ.get("CUCLARK_BENCH_READS", 10_000_000)))
     ap.add_argument("--pct-random", type=int, default=10)
+    ap.add_argument("--sub-per-10k", type=int, default=0,
+                    help="substitution errors per 10,000 bases of the sampled reads (configs[2] uses 100 = 1%%)")
     ap.add_argument("--cpu-targets", type=int, default=8, help="targets of the CPU baseline's (smaller) database")
     ap.add_argument("--cpu-reads", type=int, default=400_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--ref-lookup", action="store_true",
+                    help="also time the reference's own hTable::find (oracle/_ref) on the CPU sample (~2 min)")
     ap.add_argument("--chunk-mb", type=int, default=64, help="text pipeline: MiB of text per chunk")
     ap.add_argument("--slots", type=int, default=4, help="text pipeline: chunks in flight")
     ap.add_argument("--layout", type=int, default=int(os.environ.get("CUCLARK_BENCH_LAYOUT", 0)),
@@ -166,6 +170,43 @@ def cpu_step(orc, db, data, n_targets, threads):
     return dt, lookups, n
 
 
+def reference_lookup_leg(orc, db, data, threads: int):
+    """Host baseline B2 (BASELINE.md section 3): the reference's OWN host table — hTable::read + hTable::find
+    (src/hashTable_hh.hh:476-513, 666-946) compiled from /root/reference into oracle/_ref/libref_lookup_full.so —
+    over every k-mer of the sample reads, OpenMP over k-mers. Opt-in (--ref-lookup): writing the 1.6 GB .sz file and
+    the reference's 25.8 GB empty table take about two minutes."""
+    import shutil
+    import tempfile
+    from oracle import dbtools
+    from oracle.binding import HTSIZE_FULL, RefLookup
+    km, lb = db.entries()
+    sz, ky, lbl = dbtools.entries_to_arrays(km, lb, HTSIZE_FULL, 4)
+    d = tempfile.mkdtemp(prefix="cuclark_b2_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    try:
+        base = os.path.join(d, "db")
+        dbtools.write_db_files(base, sz, ky, lbl)
+        del sz, ky, lbl
+        t0 = time.time()
+        ref = RefLookup(light=False).open(base, K, 1, threads)
+        load_s = time.time() - t0
+        ix, buf = orc.index(data, threads)
+        ptr, cont = orc.pack(ix, buf, K)
+        kmers = orc.extract(ptr, cont, K)
+        orc.free_index(ix)
+        ref.query(kmers[:200_000], threads)
+        t0 = time.perf_counter()
+        out, hits = ref.query(kmers, threads)
+        dt = time.perf_counter() - t0
+        exp, _ = db.query(kmers, threads)
+        same = bool(np.array_equal(out, exp))
+        ref.close()
+        return {"value": kmers.size / dt, "unit": "lookups/s", "cores": threads, "kind": "reference",
+                "what": "hTable::find of the reference (oracle/_ref/libref_lookup_full.so), stage 3 only, OpenMP over k-mers",
+                "lookups": int(kmers.size), "hits": int(hits), "table_load_s": load_s, "equals_port": same}
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
 def run_reference(args, rank: int):
     """--impl reference: the reference algorithm on the host cores (the oracle port)."""
     if rank != 0:
@@ -199,7 +240,8 @@ def run_reference(args, rank: int):
 def workload_config(args, world):
     return {"workload": f"config2: cuCLARK k=31, synthetic DB {args.targets} targets x 4 Mbp "
                         f"(~{args.targets * (GENOME_LEN - K + 1) / 1e9:.2f} G 31-mers), "
-                        f"{args.reads} x {READ_LEN} bp single-end reads per GPU, {args.pct_random}% random",
+                        f"{args.reads} x {READ_LEN} bp single-end reads per GPU, {args.pct_random}% random"
+                        + (f", {args.sub_per_10k / 100:g}% substitutions" if args.sub_per_10k else ""),
             "k": K, "targets": args.targets, "reads_per_gpu": args.reads, "read_len": READ_LEN,
             "mode": ("single GPU" if world == 1 else
                      "table-partitioned, rows exchanged over NCCL all-to-all" if args.mode == "table"
@@ -246,7 +288,7 @@ def run_b200(args):
     ts = torch.cuda.Stream()
     stream = ts.cuda_stream
     # rank r classifies reads [r*n, (r+1)*n) of the global read set
-    g.synth_reads_device(READ_SEED, DB_SEED, T, GENOME_LEN, rank * n, n, READ_LEN, args.pct_random, 0,
+    g.synth_reads_device(READ_SEED, DB_SEED, T, GENOME_LEN, rank * n, n, READ_LEN, args.pct_random, args.sub_per_10k,
                          d_ptr.data_ptr(), d_cont.data_ptr(), stream)
     g.stats(sync_stream=stream, sync=True)
 
@@ -335,7 +377,7 @@ def run_b200(args):
     if not args.no_e2e:
         rec = 16 + 2 * READ_LEN
         d_text = torch.empty(n * rec, dtype=torch.uint8, device="cuda")
-        g.synth_fastq_device(READ_SEED, DB_SEED, T, GENOME_LEN, rank * n, n, READ_LEN, args.pct_random, 0,
+        g.synth_fastq_device(READ_SEED, DB_SEED, T, GENOME_LEN, rank * n, n, READ_LEN, args.pct_random, args.sub_per_10k,
                              d_text.data_ptr(), stream)
         g.stats(sync_stream=stream, sync=True)
         h_text = torch.empty(n * rec, dtype=torch.uint8, pin_memory=True)
@@ -418,7 +460,8 @@ def run_b200(args):
                          "random_access_peak_source": "measured live: 2^28 random 32 B sector loads over the same table"},
             "clocks": clocks,
             "gpu_launches": args.steps * 2,   # k_classify + k_classify_dense per step (plus one memset node)
-            "parity_properties": {"classified_frac": classified, "expected_classified_frac": 1 - args.pct_random / 100,
+            "parity_properties": {"classified_frac": classified,
+                                  "expected_classified_frac": (1 - args.pct_random / 100) if not args.sub_per_10k else None,
                                   "reads_with_all_kmers_hit_frac": full_hits},
         }
         if e2e_text:
@@ -443,6 +486,11 @@ def run_b200(args):
                 "sample": f"{args.cpu_reads} x {READ_LEN} bp reads against a {args.cpu_targets} x 4 Mbp "
                           f"({db.size / 1e6:.0f} M 31-mer) database in the reference's table layout; "
                           f"index+pack+extract+lookup+histogram+top-2 (oracle port, OpenMP)"}
+            if args.ref_lookup:
+                try:
+                    line["cpu_baseline"]["reference_lookup"] = reference_lookup_leg(orc, db, data, threads)
+                except Exception as e:      # oracle/_ref is built where /root/reference exists
+                    line["cpu_baseline"]["reference_lookup"] = {"unavailable": repr(e)}
         print(json.dumps(line), flush=True)
     g.close()
     if world > 1:

@@ -507,7 +507,9 @@ int finish_build(cuclark_db* db, const Geometry& g, BuildBuffers& b, BuildCtx& x
     const uint32_t n_ovf_entries = flags[0];
     uint64_t n_ovf = 0;
     if (n_ovf_entries) {
-        n_ovf = (uint64_t)((double)n_ovf_entries / (g.layout == LAYOUT_LOCAL ? OVF_LOAD_LOCAL : OVF_LOAD)) + 64;
+        double ovf_load = g.layout == LAYOUT_LOCAL ? OVF_LOAD_LOCAL : OVF_LOAD;
+        if (const char* e = getenv("CUCLARK_OVF_LOAD")) { const double v = atof(e); if (v >= 0.2 && v <= 2.4) ovf_load = v; }   // tuning knob
+        n_ovf = (uint64_t)((double)n_ovf_entries / ovf_load) + 64;
         if (cudaMalloc(&b.ovf, n_ovf * 32) != cudaSuccess) { cudaGetLastError(); set_error("cudaMalloc of overflow table failed"); return CUCLARK_ERR_NOMEM; }
         CK(cudaMalloc(&b.ovf_cnt8, (n_ovf / 4 + 1) * 4));
         CK(cudaMemset(b.ovf_cnt8, 0, (n_ovf / 4 + 1) * 4));
