@@ -17,10 +17,11 @@ table, the reads are split over the ranks, no collective on the data path
 ("scaling": "weak": every rank classifies --reads reads).
 
 Output: ONE JSON line on rank 0. `value` = lookups/s with inputs resident in HBM;
-`e2e` = the same through the batch API with pinned HOST buffers (H2D of the packed
-reads and D2H of the results inside the timed region); `roofline` for the classify
-kernel (32 algorithmic bytes per lookup); `cpu_baseline` = the oracle port on the
-host cores on a bounded sample (N=1 only).
+`e2e` = the same through the public text call with pinned HOST buffers (FASTQ bytes in,
+CSV bytes out; H2D and D2H inside the timed region), `e2e_packed` through the batch API
+with packed reads; `roofline` for the classify kernel (32 algorithmic bytes per lookup);
+`cpu_baseline` = the oracle port of the whole path on the host cores on a bounded sample,
+with the reference's own hTable::find beside it as `reference_lookup` (N=1 only).
 """
 from __future__ import annotations
 
@@ -59,8 +60,8 @@ def parse():
     ap.add_argument("--cpu-reads", type=int, default=400_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--ref-lookup", action="store_true",
-                    help="also time the reference's own hTable::find (oracle/_ref) on the CPU sample (~2 min)")
+    ap.add_argument("--no-ref-lookup", action="store_true",
+                    help="skip the second host baseline: the reference's own hTable::find (oracle/_ref) on the CPU sample (~45 s)")
     ap.add_argument("--chunk-mb", type=int, default=64, help="text pipeline: MiB of text per chunk")
     ap.add_argument("--slots", type=int, default=4, help="text pipeline: chunks in flight")
     ap.add_argument("--layout", type=int, default=int(os.environ.get("CUCLARK_BENCH_LAYOUT", 0)),
@@ -173,8 +174,8 @@ def cpu_step(orc, db, data, n_targets, threads):
 def reference_lookup_leg(orc, db, data, threads: int):
     """Host baseline B2 (BASELINE.md section 3): the reference's OWN host table — hTable::read + hTable::find
     (src/hashTable_hh.hh:476-513, 666-946) compiled from /root/reference into oracle/_ref/libref_lookup_full.so —
-    over every k-mer of the sample reads, OpenMP over k-mers. Opt-in (--ref-lookup): writing the 1.6 GB .sz file and
-    the reference's 25.8 GB empty table take about two minutes."""
+    over every k-mer of the sample reads, OpenMP over k-mers. Writing the 1.6 GB .sz file and filling the reference's
+    25.8 GB empty table take most of a minute (--no-ref-lookup skips the leg)."""
     import shutil
     import tempfile
     from oracle import dbtools
@@ -486,7 +487,7 @@ def run_b200(args):
                 "sample": f"{args.cpu_reads} x {READ_LEN} bp reads against a {args.cpu_targets} x 4 Mbp "
                           f"({db.size / 1e6:.0f} M 31-mer) database in the reference's table layout; "
                           f"index+pack+extract+lookup+histogram+top-2 (oracle port, OpenMP)"}
-            if args.ref_lookup:
+            if not args.no_ref_lookup and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_lookup_full.so")):
                 try:
                     line["cpu_baseline"]["reference_lookup"] = reference_lookup_leg(orc, db, data, threads)
                 except Exception as e:      # oracle/_ref is built where /root/reference exists
