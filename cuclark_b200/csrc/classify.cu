@@ -27,7 +27,10 @@ namespace cuclark {
 
 namespace {
 
-constexpr int WARPS_PER_BLOCK = 8;
+#ifndef CUCLARK_WPB
+#define CUCLARK_WPB 8
+#endif
+constexpr int WARPS_PER_BLOCK = CUCLARK_WPB;
 constexpr int TSLOTS = 64;            // per-warp hash slots
 constexpr int ILP_ROUNDS = 4;         // independent probes per lane
 #ifndef CUCLARK_ILP_LOCAL
@@ -280,12 +283,11 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, LAYOUT == LAYOUT_LOCAL ?
                                 my_lookups += valid;
                                 if (live[j]) sec[j] = load_sector_line(T.buckets + 2 * (uint64_t)lb[j]);
                             }
-                            // Home sectors are consumed row by row (the hit accounting of row j runs while the
-                            // loads of the later rows are still in flight); a lane whose k-mer may have spilled
-                            // issues its first overflow probe at once and counts as "no hit" for now. The
-                            // overflow probes are consumed in a second sweep: hit counts are additive, so a
-                            // row may be accounted in two parts. (The clumped fill of the lines spills ~15% of
-                            // the entries; probing them one after the other would cost a round trip each.)
+                            // Home sectors are matched row by row; a lane whose k-mer may have spilled issues its
+                            // first overflow probe at once, so that the overflow probes of all rows are in
+                            // flight together, and every row is accounted once its overflow probes are back.
+                            // (The clumped fill of the lines spills ~15% of the entries; probing them one after
+                            // the other would cost a memory round trip each.)
                             bool need[ILP];
                             uint64_t ob[ILP];
 #pragma unroll
@@ -301,12 +303,11 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, LAYOUT == LAYOUT_LOCAL ?
                                     ob[j] = ovf_home(cc[j], T.n_ovf);
                                     sec[j] = load_sector(T.ovf + 2 * ob[j]);
                                 }
-                                account(label);
+                                lb[j] = label;                   // the bucket index is no longer needed
                             }
 #pragma unroll
                             for (int j = 0; j < ILP; j++) {
-                                if (!__any_sync(0xFFFFFFFFu, need[j])) continue;
-                                uint32_t label = NO_LABEL;
+                                uint32_t label = lb[j];
                                 if (need[j]) {
                                     label = match_sector<LAYOUT_WIDE>(sec[j], cc[j]);
                                     if (label == NO_LABEL && ((uint64_t)sec[j].w[4] | ((uint64_t)sec[j].w[5] << 32)) != OVF_EMPTY)
