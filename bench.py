@@ -428,6 +428,8 @@ def run_b200(args):
     f = d_final.view(n, 5).cpu().numpy().view(np.uint16)
     classified = float((f[:, 1] > 0).mean())
     full_hits = float((f[:, 2] == READ_LEN - K + 1).mean())
+    import hashlib
+    final_sha1 = hashlib.sha1(np.ascontiguousarray(f).tobytes()).hexdigest()   # same for every table layout
 
     # ---- reduce over ranks --------------------------------------------------------
     t = torch.tensor([total_ms, e2e["s"] if e2e else 0.0, e2e_text["s"] if e2e_text else 0.0],
@@ -463,7 +465,8 @@ def run_b200(args):
             "gpu_launches": args.steps * 2,   # k_classify + k_classify_dense per step (plus one memset node)
             "parity_properties": {"classified_frac": classified,
                                   "expected_classified_frac": (1 - args.pct_random / 100) if not args.sub_per_10k else None,
-                                  "reads_with_all_kmers_hit_frac": full_hits},
+                                  "reads_with_all_kmers_hit_frac": full_hits,
+                                  "final_rows_sha1_rank0": final_sha1},
         }
         if e2e_text:
             line["e2e"] = {"value": lookups_all / text_s_max, "unit": "lookups/s", "reads_per_s": reads_all / text_s_max,
