@@ -416,7 +416,7 @@ Geometry choose_geometry(const cuclark_config& cfg, uint64_t n_entries, double g
     // automatic choice: minimizer lines for a single-device table that fills them (at bacterial scale they
     // serve ~1.25x the lookups of the hashed sectors; a small database would pay the minimum size for nothing)
     if (layout == 0 && allow_auto_local && cfg.shard_count <= 1 && local_fits && cfg.bucket_load <= 0 &&
-        (double)local_min_lines(cfg.k) <= 1.25 * local_lines && !getenv("CUCLARK_NO_LOCAL"))
+        (double)local_min_lines(cfg.k) <= 1.25 * local_lines && 4.0 * local_lines < 4.2e9 && !getenv("CUCLARK_NO_LOCAL"))
         layout = LAYOUT_LOCAL;
     if (layout == LAYOUT_LOCAL && local_fits) {
         // entries per 4-slot sector; the k-mers of a read that share a minimizer arrive in
@@ -738,7 +738,7 @@ int table_build_from_arrays(cuclark_db* db, const uint8_t* sz_in, const void* ky
         BuildBuffers bb;
         BuildCtx x{};
         rc = alloc_build(g, kept / (db->cfg.shard_count > 1 ? db->cfg.shard_count : 1), bb, x, H, db->cfg.k);
-        if (rc != CUCLARK_OK) { bb.free_all(); if (is_auto_local && rc == CUCLARK_ERR_NOMEM) { rc = CUCLARK_ERR_BUILD; continue; } break; }
+        if (rc != CUCLARK_OK) { bb.free_all(); if (is_auto_local && rc != CUCLARK_ERR_ARG) { cudaGetLastError(); rc = CUCLARK_ERR_BUILD; continue; } break; }
         if (cudaDeviceSynchronize() != cudaSuccess) {              // the table is initialised on the default stream
             set_error("table initialisation failed: %s", cudaGetErrorString(cudaGetLastError()));
             bb.free_all();
@@ -792,6 +792,7 @@ int table_build_from_arrays(cuclark_db* db, const uint8_t* sz_in, const void* ky
         }
         if (rc == CUCLARK_OK) rc = finish_build(db, g, bb, x, false);
         if (rc != CUCLARK_OK) bb.free_all();
+        if (is_auto_local && (rc == CUCLARK_ERR_NOMEM || rc == CUCLARK_ERR_CUDA)) { cudaGetLastError(); rc = CUCLARK_ERR_BUILD; }   // hashed retry
     }
     if (timing)
         fprintf(stderr, "[cuclark timing] database load: host pass over %llu bucket sizes %.1f ms on %d threads, "
@@ -823,7 +824,7 @@ int table_build_synthetic(cuclark_db* db, uint32_t seed, uint32_t n_targets, uin
         BuildBuffers bb;
         BuildCtx x{};
         rc = alloc_build(g, expected / (db->cfg.shard_count > 1 ? db->cfg.shard_count : 1), bb, x, db->cfg.htsize, db->cfg.k);
-        if (rc != CUCLARK_OK) { bb.free_all(); if (is_auto_local && rc == CUCLARK_ERR_NOMEM) { rc = CUCLARK_ERR_BUILD; continue; } break; }
+        if (rc != CUCLARK_OK) { bb.free_all(); if (is_auto_local && rc != CUCLARK_ERR_ARG) { cudaGetLastError(); rc = CUCLARK_ERR_BUILD; continue; } break; }
         if (light_gap > 0) {
             const uint64_t n = per_target * n_targets;
             const unsigned blocks = (unsigned)((n + 255) / 256);
@@ -843,6 +844,7 @@ int table_build_synthetic(cuclark_db* db, uint32_t seed, uint32_t n_targets, uin
         if (e != cudaSuccess) { set_error("synthetic insert failed: %s", cudaGetErrorString(e)); bb.free_all(); return CUCLARK_ERR_CUDA; }
         rc = finish_build(db, g, bb, x, true);
         if (rc != CUCLARK_OK) bb.free_all();
+        if (is_auto_local && (rc == CUCLARK_ERR_NOMEM || rc == CUCLARK_ERR_CUDA)) { cudaGetLastError(); rc = CUCLARK_ERR_BUILD; }   // hashed retry
     }
     return rc;
 }
