@@ -148,22 +148,32 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, LAYOUT == LAYOUT_LOCAL ?
                 pf_hdr = pn < en ? p.cont[pn] : 0;
                 pf_win = pn + 1 + lane < en ? p.cont[pn + 1 + lane] : 0;
             }
-            uint32_t first_label = NO_LABEL, first_cnt = 0, total = 0;
+            uint32_t first_label = NO_LABEL, first_cnt = 0, total = 0, my_same = 0;
             bool table_mode = false, overflow = false;
             bool first_part = true;
             // hits of one row of 32 k-mers into the read's counters (warp-collective)
+            // hits of one row of 32 k-mers into the read's counters (warp-collective). While every hit of the
+            // read went to ONE target (the usual case) each lane just counts its own hits: one vote per row.
             auto account = [&](const uint32_t label) {
-                const uint32_t hitmask = __ballot_sync(0xFFFFFFFFu, label != NO_LABEL);
-                if (!hitmask) return;
-                total += __popc(hitmask);
+                uint32_t hitmask = 0;
                 if (!table_mode) {
-                    if (first_label == NO_LABEL) first_label = __shfl_sync(0xFFFFFFFFu, label, __ffs(hitmask) - 1);
-                    const uint32_t same = __ballot_sync(0xFFFFFFFFu, label == first_label);
-                    if (same == hitmask) { first_cnt += __popc(same); return; }
+                    if (first_label == NO_LABEL) {
+                        hitmask = __ballot_sync(0xFFFFFFFFu, label != NO_LABEL);
+                        if (!hitmask) return;
+                        first_label = __shfl_sync(0xFFFFFFFFu, label, __ffs(hitmask) - 1);
+                    }
+                    const bool hit = label != NO_LABEL;
+                    if (!__any_sync(0xFFFFFFFFu, hit && label != first_label)) { my_same += hit; return; }
+                    // a second target: fold the per-lane counts and continue in the shared-memory table
+                    first_cnt = __reduce_add_sync(0xFFFFFFFFu, my_same);
+                    total = first_cnt;
                     table_mode = true;
                     if (lane == 0 && first_cnt) tab_add(tkey, tcnt, first_label, first_cnt);
                     __syncwarp();
                 }
+                hitmask = __ballot_sync(0xFFFFFFFFu, label != NO_LABEL);
+                if (!hitmask) return;
+                total += __popc(hitmask);
                 const uint32_t grp = __match_any_sync(0xFFFFFFFFu, label);
                 bool ok = true;
                 if (label != NO_LABEL && lane == __ffs(grp) - 1) ok = tab_add(tkey, tcnt, label, __popc(grp));
@@ -270,14 +280,14 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, LAYOUT == LAYOUT_LOCAL ?
                                 const uint64_t z0 = shfl64(zs[j], src), z1 = shfl64(zs[j + 1], src);
                                 const uint64_t zf = (pos >> 5) == (uint32_t)j ? z0 : z1;
                                 const int o_read = (int)((pos - (uint32_t)(32 * j + lane)) & 7u);
-                                uint64_t zq, line;
-                                divmod_M(zf & ((1ull << 62) - 1), T.NL, T.magicNL, zq, line);
+                                uint32_t zq, line;
+                                local_divmod(zf & ((1ull << 62) - 1), (uint32_t)T.NL, T.nl_m32, T.nl_sh, zq, line);
                                 const int o_c = is_fwd ? o_read : LOCAL_W - 1 - o_read;
                                 const bool f = (zf >> (is_fwd ? 63 : 62)) & 1ull;
                                 const uint32_t rest = local_rest(c, o_c, m);
                                 q[j] = (uint64_t)local_key_lo(zq, rest) | ((uint64_t)local_key_hi(rest, o_c, f) << 32);
                                 cc[j] = c;
-                                const uint64_t lb64 = line * 4 + (uint64_t)(o_c & 3) - T.lo;
+                                const uint64_t lb64 = (uint64_t)line * 4 + (uint64_t)(o_c & 3) - T.lo;
                                 lb[j] = (uint32_t)lb64;
                                 live[j] = valid && lb64 < T.n_local;
                                 my_lookups += valid;
@@ -363,7 +373,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, LAYOUT == LAYOUT_LOCAL ?
         }
         uint32_t v_sum, v_i1, v_h1, v_i2, v_h2;
         if (!table_mode) {
-            const uint32_t h = first_cnt & 0xFFFFu;
+            const uint32_t h = __reduce_add_sync(0xFFFFFFFFu, my_same) & 0xFFFFu;
             v_sum = h; v_i1 = h ? first_label + 1 : 0; v_h1 = h; v_i2 = 0; v_h2 = 0;
             if (ROWS) {
                 for (int i = lane; i < pitch; i += 32) {

@@ -75,6 +75,8 @@ struct TableView {
     uint64_t n_ovf;         // buckets in the overflow table
     uint64_t NL;            // LOCAL: number of 128-byte lines (M = 4 NL), and floor(2^64 / NL)
     uint64_t magicNL;
+    uint32_t nl_m32;        // LOCAL: floor(2^(32 + nl_sh) / NL) for local_divmod()
+    int nl_sh;              //        max(0, 2m - 32)
     int layout;
     int k;
 };
@@ -142,6 +144,20 @@ __host__ __device__ __forceinline__ uint64_t local_unmix(uint64_t z, int nbits) 
 __host__ __device__ __forceinline__ uint32_t local_order(uint64_t z, int nbits) {
     const uint32_t h = (uint32_t)(z >> (nbits - 24));
     return h > LOCAL_ORDER_MAX ? LOCAL_ORDER_MAX : h;
+}
+// (zq, line) = divmod(z, NL) for z < 4^m in 32-bit arithmetic: the quotient estimate from the top 32 bits of z and
+// m32 = floor(2^(32+sh) / NL) is at most 2 too small (NL >= 2^(sh+13)), and 3 NL < 2^32, so the remainder lives in 32 bits
+__host__ __device__ __forceinline__ void local_divmod(uint64_t z, uint32_t NL, uint32_t m32, int sh, uint32_t& zq, uint32_t& line) {
+#ifdef __CUDA_ARCH__
+    uint32_t q = __umulhi((uint32_t)(z >> sh), m32);
+#else
+    uint32_t q = (uint32_t)(((uint64_t)(uint32_t)(z >> sh) * m32) >> 32);
+#endif
+    uint32_t r = (uint32_t)z - q * NL;
+    if (r >= NL) { r -= NL; q++; }
+    if (r >= NL) { r -= NL; q++; }
+    zq = q;
+    line = r;
 }
 // canonical m-mer at offset o of the 2k-bit code y (first nucleotide in the high bits);
 // fwd tells whether the form standing in y is the strictly smaller one
@@ -225,11 +241,11 @@ __device__ __forceinline__ uint32_t match_sector(const Sector& s, uint64_t key) 
         }
     } else if (LAYOUT == LAYOUT_LOCAL) {
         const uint32_t k32 = (uint32_t)key;
-        const uint32_t eqhi = __vcmpeq4(s.w[6], (uint32_t)(key >> 32) * 0x01010101u);   // 0xFF where the high byte matches
+        const uint32_t nehi = ~__vcmpeq4(s.w[6], (uint32_t)(key >> 32) * 0x01010101u);  // 0x00 where the high byte matches
 #pragma unroll
         for (int i = 0; i < LOCAL_SLOTS; i++) {
             const uint32_t lw = s.w[4 + (i >> 1)];
-            if (s.w[i] == k32 && ((eqhi >> (8 * i)) & 1u)) label = (i & 1) ? (lw >> 16) : (lw & 0xFFFFu);
+            if (((s.w[i] ^ k32) | ((nehi >> (8 * i)) & 0xFFu)) == 0u) label = (i & 1) ? (lw >> 16) : (lw & 0xFFFFu);
         }
     } else {
 #pragma unroll

@@ -392,6 +392,15 @@ uint64_t local_min_lines(int k) {
     return mbits > LOCAL_ZQ_BITS ? (1ull << (mbits - LOCAL_ZQ_BITS)) : 1;
 }
 
+// constants of local_divmod() (common.cuh) for this table
+void set_local_divmod(TableView& v) {
+    v.nl_m32 = 0; v.nl_sh = 0;
+    if (v.layout != LAYOUT_LOCAL || v.NL < 2) return;
+    const int mbits = 2 * (v.k - LOCAL_W + 1);
+    v.nl_sh = mbits > 32 ? mbits - 32 : 0;
+    v.nl_m32 = (uint32_t)((((__uint128_t)1) << (32 + v.nl_sh)) / v.NL);
+}
+
 uint64_t pow4(int k) { return k >= 32 ? 0 : (1ull << (2 * k)); }   // 0 means 2^64
 
 Geometry choose_geometry(const cuclark_config& cfg, uint64_t n_entries, double grow, bool allow_auto_local = true) {
@@ -567,6 +576,7 @@ int finish_build(cuclark_db* db, const Geometry& g, BuildBuffers& b, BuildCtx& x
     db->view.k = db->cfg.k;
     db->view.NL = g.NL;
     db->view.magicNL = g.NL ? (uint64_t)((((__uint128_t)1) << 64) / g.NL) : 0;
+    set_local_divmod(db->view);
     b.free_temp();
     return CUCLARK_OK;
 }
@@ -1035,7 +1045,7 @@ int table_load(cuclark_db* db, const char* path, const char* src_base, int sfact
     db->view.M = h.M; db->view.magic = (uint64_t)((((__uint128_t)1) << 64) / h.M);
     db->view.lo = h.lo; db->view.n_local = h.n_local; db->view.n_ovf = h.n_ovf;
     db->view.layout = (int)h.layout; db->view.k = db->cfg.k;
-    if (h.layout == LAYOUT_LOCAL) { db->view.NL = h.M / 4; db->view.magicNL = (uint64_t)((((__uint128_t)1) << 64) / db->view.NL); }
+    if (h.layout == LAYOUT_LOCAL) { db->view.NL = h.M / 4; db->view.magicNL = (uint64_t)((((__uint128_t)1) << 64) / db->view.NL); set_local_divmod(db->view); }
     db->n_entries = h.n_entries; db->n_spilled = h.n_spilled; db->n_spill_buckets = h.n_spill_buckets;
     db->src_sfactor = (int)h.sfactor;
     for (int i = 0; i < 3; i++) db->src_bytes[i] = h.src_bytes[i];

@@ -53,6 +53,12 @@ extern "C" long shim_local_check(int k, uint64_t NL, long n, int* first_bad) {
         const uint32_t rest = local_rest(c, o_c, m);
         const uint64_t q = (uint64_t)local_key_lo(z / NL, rest) | ((uint64_t)local_key_hi(rest, o_c, f) << 32);
         if (q != key || (z % NL) * 4 + (uint64_t)(o_c & 3) != sec) { *first_bad = 4; return t; }
+        // the kernel's 32-bit divmod
+        const int sh = 2 * m > 32 ? 2 * m - 32 : 0;
+        const uint32_t m32 = (uint32_t)((((__uint128_t)1) << (32 + sh)) / NL);
+        uint32_t dq, dr;
+        local_divmod(z, (uint32_t)NL, m32, sh, dq, dr);
+        if (dq != z / NL || dr != z % NL) { *first_bad = 5; return t; }
     }
     *first_bad = 0;
     return ties;
