@@ -34,7 +34,7 @@ constexpr int WARPS_PER_BLOCK = CUCLARK_WPB;
 constexpr int TSLOTS = 64;            // per-warp hash slots
 constexpr int ILP_ROUNDS = 4;         // independent probes per lane
 #ifndef CUCLARK_ILP_LOCAL
-#define CUCLARK_ILP_LOCAL 2
+#define CUCLARK_ILP_LOCAL 1
 #endif
 #ifndef CUCLARK_LOCAL_MIN_BLOCKS
 #define CUCLARK_LOCAL_MIN_BLOCKS 4
@@ -210,6 +210,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, LAYOUT == LAYOUT_LOCAL ?
                         Sector sec[ILP];
                         bool live[ILP];
                         uint64_t cc[LAYOUT == LAYOUT_LOCAL ? ILP : 1];   // LOCAL: the k-mer itself (overflow key)
+                        Sector secb[LAYOUT == LAYOUT_LOCAL ? ILP : 1];   // LOCAL: sector of the second candidate line
                         if (LAYOUT == LAYOUT_LOCAL) {
                             // ---- minimizer of every k-mer of the ILP rows. Each lane hashes the FIRST m-mer of
                             // its position (rows r0..r0+ILP: the windows of the last row reach 7 positions
@@ -287,41 +288,27 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, LAYOUT == LAYOUT_LOCAL ?
                                 const uint32_t rest = local_rest(c, o_c, m);
                                 q[j] = (uint64_t)local_key_lo(zq, rest) | ((uint64_t)local_key_hi(rest, o_c, f) << 32);
                                 cc[j] = c;
+                                // the sector of the A line and of the B line (second choice of the table builder):
+                                // two independent loads, no dependent second round trip
                                 const uint64_t lb64 = (uint64_t)line * 4 + (uint64_t)(o_c & 3) - T.lo;
                                 lb[j] = (uint32_t)lb64;
                                 live[j] = valid && lb64 < T.n_local;
                                 my_lookups += valid;
-                                if (live[j]) sec[j] = load_sector_line(T.buckets + 2 * (uint64_t)lb[j]);
+                                uint32_t rel_b = line - T.line_lo + local_alt_step(zq, T.line_n);
+                                if (rel_b >= T.line_n) rel_b -= T.line_n;
+                                if (live[j]) {
+                                    sec[j] = load_sector_line(T.buckets + 2 * (uint64_t)lb[j]);
+                                    secb[j] = load_sector_line(T.buckets + 2 * ((uint64_t)rel_b * 4 + (uint64_t)(o_c & 3)));
+                                }
                             }
-                            // Home sectors are matched row by row; a lane whose k-mer may have spilled issues its
-                            // first overflow probe at once, so that the overflow probes of all rows are in
-                            // flight together, and every row is accounted once its overflow probes are back.
-                            // (The clumped fill of the lines spills ~15% of the entries; probing them one after
-                            // the other would cost a memory round trip each.)
-                            bool need[ILP];
-                            uint64_t ob[ILP];
 #pragma unroll
                             for (int j = 0; j < ILP; j++) {
                                 uint32_t label = NO_LABEL;
-                                need[j] = false;
                                 if (live[j]) {
                                     label = match_sector<LAYOUT_LOCAL>(sec[j], q[j]);
-                                    need[j] = label == NO_LABEL && sector_overflowed(sec[j]);
-                                    if (label >= p.n_targets) label = NO_LABEL;
-                                }
-                                if (need[j]) {
-                                    ob[j] = ovf_home(cc[j], T.n_ovf);
-                                    sec[j] = load_sector(T.ovf + 2 * ob[j]);
-                                }
-                                lb[j] = label;                   // the bucket index is no longer needed
-                            }
-#pragma unroll
-                            for (int j = 0; j < ILP; j++) {
-                                uint32_t label = lb[j];
-                                if (need[j]) {
-                                    label = match_sector<LAYOUT_WIDE>(sec[j], cc[j]);
-                                    if (label == NO_LABEL && ((uint64_t)sec[j].w[4] | ((uint64_t)sec[j].w[5] << 32)) != OVF_EMPTY)
-                                        label = ovf_lookup_from(T, cc[j], ob[j] + 1 == T.n_ovf ? 0 : ob[j] + 1, 1);
+                                    if (label == NO_LABEL) label = match_sector<LAYOUT_LOCAL>(secb[j], q[j] | ((uint64_t)LOCAL_ALT_BIT << 32));
+                                    // both candidate sectors full at build time: the k-mer may be in the overflow table (rare)
+                                    if (label == NO_LABEL && sector_overflowed(sec[j]) && sector_overflowed(secb[j])) label = ovf_lookup(T, cc[j]);
                                     if (label >= p.n_targets) label = NO_LABEL;
                                 }
                                 account(label);

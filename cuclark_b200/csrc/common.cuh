@@ -27,6 +27,10 @@
 //     into one line request instead of one random sector each. The slot still identifies the
 //     k-mer exactly: key = mix(minimizer) div NL (<= 19 bit) | the 7 other nucleotides (14 bit)
 //     | offset (3 bit) | strand of the minimizer (1 bit) = 37 bit.
+//     TWO candidate lines per minimizer (A = mix mod NL, B = A + step(key) inside the shard): an entry
+//     goes to the emptier one; a lookup loads the sector of both (independent loads, no second round
+//     trip) and a bit of the key tells an entry living in its B line from one living in its A line.
+//     Lines fill in clumps of ~4.5 entries, one choice would overflow ~16% of the entries.
 //     word 0..3   key[0..3] low 32 bits      (all-ones + high byte 0xFF = empty)
 //     word 4      label[0] | label[1] << 16
 //     word 5      label[2] | label[3] << 16
@@ -77,6 +81,7 @@ struct TableView {
     uint64_t magicNL;
     uint32_t nl_m32;        // LOCAL: floor(2^(32 + nl_sh) / NL) for local_divmod()
     int nl_sh;              //        max(0, 2m - 32)
+    uint32_t line_lo, line_n;   // LOCAL: this shard's lines [line_lo, line_lo + line_n)
     int layout;
     int k;
 };
@@ -198,6 +203,48 @@ __host__ __device__ __forceinline__ void local_locate(uint64_t c, int k, uint64_
     sector = line * 4 + (uint64_t)(bo & 3);
     key = (uint64_t)local_key_lo(zq, rest) | ((uint64_t)local_key_hi(rest, bo, bf) << 32);
 }
+// ---- second candidate line -----------------------------------------------------------
+constexpr uint32_t LOCAL_ALT_BIT = 1u << 5;            // in the key's high byte: the entry lives in its B line
+// distance from a k-mer's A line to its B line, inside its shard's nloc lines; a function of the part of
+// the mixed minimizer that the key keeps (zq), so that the A line is recoverable from (B line, key)
+__host__ __device__ __forceinline__ uint32_t local_alt_step(uint32_t zq, uint32_t nloc) {
+    if (nloc < 2) return 0;
+    const uint32_t h = zq * 0x9E3779B1u + 0x7F4A7C15u;
+#ifdef __CUDA_ARCH__
+    return 1u + __umulhi(h, nloc - 1u);
+#else
+    return 1u + (uint32_t)(((uint64_t)h * (nloc - 1u)) >> 32);
+#endif
+}
+// B line (global index) of the k-mer with A line `line_a` and key part zq; shard lines [line_lo, line_lo + line_n)
+__host__ __device__ __forceinline__ uint64_t local_alt_line(uint64_t line_a, uint32_t zq, uint64_t line_lo, uint32_t line_n) {
+    uint64_t rel = line_a - line_lo + local_alt_step(zq, line_n);
+    if (rel >= line_n) rel -= line_n;
+    return line_lo + rel;
+}
+__host__ __device__ __forceinline__ uint64_t local_alt_line_inv(uint64_t line_b, uint32_t zq, uint64_t line_lo, uint32_t line_n) {
+    const uint32_t step = local_alt_step(zq, line_n);
+    uint64_t rel = line_b - line_lo;
+    rel = rel >= step ? rel - step : rel + line_n - step;
+    return line_lo + rel;
+}
+// both candidate sectors (global indices) of c; sec_b == sec_a when the A line is not in this shard
+__host__ __device__ __forceinline__ void local_locate2(uint64_t c, int k, uint64_t NL, uint64_t line_lo, uint32_t line_n,
+                                                       uint64_t& sec_a, uint64_t& sec_b, uint64_t& key) {
+    local_locate(c, k, NL, sec_a, key);
+    const uint64_t line_a = sec_a >> 2;
+    sec_b = sec_a;
+    if (line_a - line_lo < line_n)
+        sec_b = local_alt_line(line_a, (uint32_t)(key & ((1ull << LOCAL_ZQ_BITS) - 1)), line_lo, line_n) * 4 + (sec_a & 3);
+}
+// the k-mer stored as `key` (with or without LOCAL_ALT_BIT) in a sector of global line `line`
+__host__ __device__ __forceinline__ uint64_t local_rebuild(uint64_t line, uint64_t key, int k, uint64_t NL);
+__host__ __device__ __forceinline__ uint64_t local_rebuild2(uint64_t line, uint64_t key, int k, uint64_t NL, uint64_t line_lo, uint32_t line_n) {
+    const uint64_t alt = (uint64_t)LOCAL_ALT_BIT << 32;
+    if (key & alt) line = local_alt_line_inv(line, (uint32_t)(key & ((1ull << LOCAL_ZQ_BITS) - 1)), line_lo, line_n);
+    return local_rebuild(line, key & ~alt, k, NL);
+}
+
 // inverse of local_locate: the canonical k-mer stored as `key` in (a sector of) `line`
 __host__ __device__ __forceinline__ uint64_t local_rebuild(uint64_t line, uint64_t key, int k, uint64_t NL) {
     const int m = k - LOCAL_W + 1;
@@ -309,8 +356,18 @@ __device__ __forceinline__ uint32_t ovf_lookup(const TableView& t, uint64_t c) {
 template <int LAYOUT>
 __device__ __forceinline__ uint32_t table_lookup(const TableView& t, uint64_t c) {
     uint64_t q, b;
-    if (LAYOUT == LAYOUT_LOCAL) local_locate(c, t.k, t.NL, b, q);
-    else divmod_M(c, t.M, t.magic, q, b);
+    if (LAYOUT == LAYOUT_LOCAL) {
+        uint64_t sa, sb;
+        local_locate2(c, t.k, t.NL, t.line_lo, t.line_n, sa, sb, q);
+        const uint64_t la = sa - t.lo;
+        if (la >= t.n_local) return NO_LABEL;       // other shard
+        const Sector A = load_sector(t.buckets + 2 * la), B = load_sector(t.buckets + 2 * (sb - t.lo));
+        uint32_t label = match_sector<LAYOUT_LOCAL>(A, q);
+        if (label == NO_LABEL) label = match_sector<LAYOUT_LOCAL>(B, q | ((uint64_t)LOCAL_ALT_BIT << 32));
+        if (label == NO_LABEL && sector_overflowed(A) && sector_overflowed(B)) label = ovf_lookup(t, c);
+        return label;
+    }
+    divmod_M(c, t.M, t.magic, q, b);
     const uint64_t lb = b - t.lo;
     if (lb >= t.n_local) return NO_LABEL;           // other shard (b < lo wraps around)
     const Sector s = load_sector(t.buckets + 2 * lb);

@@ -88,6 +88,32 @@ template <int LAYOUT>
 __device__ __forceinline__ bool insert_home(const BuildCtx& x, uint64_t c, uint32_t label) {
     constexpr uint32_t SLOTS = LAYOUT == LAYOUT_NARROW ? NARROW_SLOTS : LAYOUT == LAYOUT_LOCAL ? LOCAL_SLOTS : WIDE_SLOTS;
     uint64_t q, b;
+    if (LAYOUT == LAYOUT_LOCAL) {
+        // two candidate sectors (A line, B line): take the emptier one, the other if that one fills up
+        // under our feet; the overflow table only when both are full
+        uint64_t sa, sb;
+        local_locate2(c, x.k, x.NL, x.lo >> 2, (uint32_t)(x.n_local >> 2), sa, sb, q);
+        const uint64_t la = sa - x.lo, lbb = sb - x.lo;
+        if (la >= x.n_local) return false;           // homed in another shard
+        const uint32_t ca = (__ldcg(&x.cnt8[la >> 2]) >> (8 * (uint32_t)(la & 3))) & 0xFFu;
+        const uint32_t cb = (__ldcg(&x.cnt8[lbb >> 2]) >> (8 * (uint32_t)(lbb & 3))) & 0xFFu;
+        const bool b_first = cb < ca && lbb != la;
+        for (int t = 0; t < 2; t++) {
+            const bool use_b = (t == 0) == b_first;
+            if (use_b && lbb == la) continue;
+            const uint64_t l = use_b ? lbb : la;
+            if (((__ldcg(&x.cnt8[l >> 2]) >> (8 * (uint32_t)(l & 3))) & 0xFFu) >= SLOTS) continue;   // full: do not wrap the byte
+            const uint32_t slot = claim_slot(x.cnt8, x.flags, l);
+            if (slot < SLOTS) {
+                write_slot<LAYOUT>(x.table, l, slot, use_b ? q | ((uint64_t)LOCAL_ALT_BIT << 32) : q, label);
+                return true;
+            }
+        }
+        const uint32_t i = atomicAdd(&x.flags[0], 1u);
+        if (i < x.ovf_cap) { x.ovf_c[i] = c; x.ovf_l[i] = (uint16_t)label; }
+        else atomicOr(&x.flags[1], ERR_OVF_LIST);
+        return true;
+    }
     home_of<LAYOUT>(c, x.M, x.magic, x.NL, x.k, q, b);
     const uint64_t lb = b - x.lo;
     if (lb >= x.n_local) return false;               // homed in another shard
@@ -168,7 +194,13 @@ __global__ void k_place_spills(BuildCtx x, uint32_t n) {
     const uint64_t c = x.ovf_c[i];
     const uint32_t label = x.ovf_l[i];
     uint64_t q, b;
-    home_of_rt(x.layout, c, x.M, x.magic, x.NL, x.k, q, b);
+    if (x.layout == LAYOUT_LOCAL) {                  // both candidate sectors were full
+        uint64_t sb;
+        local_locate2(c, x.k, x.NL, x.lo >> 2, (uint32_t)(x.n_local >> 2), b, sb, q);
+        atomicOr(reinterpret_cast<uint32_t*>(x.table + 2 * (sb - x.lo)) + 7, 1u << 16);
+    } else {
+        home_of_rt(x.layout, c, x.M, x.magic, x.NL, x.k, q, b);
+    }
     const uint64_t lb = b - x.lo;
     atomicOr(reinterpret_cast<uint32_t*>(x.table + 2 * lb) + 7, 1u << 16);
     uint64_t ob = ovf_home(c, x.n_ovf);
@@ -291,6 +323,33 @@ __device__ __forceinline__ uint32_t ovf_scan(const uint4* ovf, uint64_t n_ovf, u
     return before;
 }
 
+// LOCAL: the copies of one k-mer (candidate sectors la / lbb, local indices; key q without the alt bit) in the
+// main table other than slot (my_lb, my_slot). Order of the copies: A slots, then B slots. Sets differ if a copy
+// carries another label, any if there is a copy at all; returns whether a copy precedes (my_lb, my_slot).
+__device__ __forceinline__ bool local_main_copies(const uint4* table, uint64_t la, uint64_t lbb, uint64_t q, uint32_t label,
+                                                  uint64_t my_lb, int my_slot, bool& differ, bool& any) {
+    bool earlier = false, passed = false;
+    any = false;
+    for (int t = 0; t < 2; t++) {
+        if (t && lbb == la) break;
+        const uint64_t l = t ? lbb : la;
+        const uint64_t key = t ? q | ((uint64_t)LOCAL_ALT_BIT << 32) : q;
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(table + 2 * l);
+        for (int s = 0; s < LOCAL_SLOTS; s++) {
+            if (l == my_lb && s == my_slot) { passed = true; continue; }
+            uint64_t kk; uint32_t ll;
+            if (!read_slot<LAYOUT_LOCAL>(w, s, kk, ll) || kk != key) continue;
+            any = true;
+            if (ll != label) differ = true;
+            if (!passed) earlier = true;
+        }
+    }
+    return earlier;
+}
+__device__ __forceinline__ bool sector_flagged(const uint4* table, uint64_t l) {
+    return (reinterpret_cast<const uint32_t*>(table + 2 * l)[7] >> 16) & 1u;
+}
+
 template <int LAYOUT>
 __global__ void k_dedupe_main(DedupeView<LAYOUT> v) {
     constexpr int SLOTS = SlotsOf<LAYOUT>::n;
@@ -303,6 +362,25 @@ __global__ void k_dedupe_main(DedupeView<LAYOUT> v) {
     bool used[SLOTS];
     for (int s = 0; s < SLOTS; s++) used[s] = read_slot<LAYOUT>(w, s, keys[s], labels[s]);
     uint32_t del = 0;
+    if (LAYOUT == LAYOUT_LOCAL) {
+        const uint64_t line_lo = v.lo >> 2;
+        const uint32_t line_n = (uint32_t)(v.n_local >> 2);
+        for (int i = 0; i < SLOTS; i++) {
+            if (!used[i]) continue;
+            const uint64_t c = local_rebuild2((lb + v.lo) >> 2, keys[i], v.k, v.NL, line_lo, line_n);
+            uint64_t sa, sb, q;
+            local_locate2(c, v.k, v.NL, line_lo, line_n, sa, sb, q);
+            bool differ = false, any;
+            const bool earlier = local_main_copies(v.table, sa - v.lo, sb - v.lo, q, labels[i], lb, i, differ, any);
+            if (v.n_ovf && sector_flagged(v.table, sa - v.lo) && sector_flagged(v.table, sb - v.lo)) {
+                uint32_t total;
+                ovf_scan(v.ovf, v.n_ovf, c, labels[i], ~0ull, 0, differ, total);
+            }
+            if (differ || earlier) del |= 1u << i;  // main copies precede overflow copies
+        }
+        v.del_main[lb] = (uint8_t)del;
+        return;
+    }
     for (int i = 0; i < SLOTS; i++) {
         if (!used[i]) continue;
         bool differ = false, earlier = false;
@@ -335,6 +413,14 @@ __global__ void k_dedupe_ovf(DedupeView<LAYOUT> v, uint64_t magic) {
         bool differ = false;
         uint32_t total;
         const uint32_t before = ovf_scan(v.ovf, v.n_ovf, c, label, ob, s, differ, total);
+        if (LAYOUT == LAYOUT_LOCAL) {               // copies in the two candidate sectors
+            uint64_t sa, sb, q;
+            local_locate2(c, v.k, v.NL, v.lo >> 2, (uint32_t)(v.n_local >> 2), sa, sb, q);
+            bool in_main;
+            local_main_copies(v.table, sa - v.lo, sb - v.lo, q, label, ~0ull, 0, differ, in_main);
+            if (differ || in_main || before) del |= 1u << s;
+            continue;
+        }
         // copies in the home bucket
         uint64_t q, b;
         home_of<LAYOUT>(c, v.M, magic, v.NL, v.k, q, b);
@@ -417,7 +503,7 @@ Geometry choose_geometry(const cuclark_config& cfg, uint64_t n_entries, double g
     // LOCAL needs at least local_min_lines(k) lines (key width); a table that would be mostly
     // empty at that size (small database at large k) uses the hashed layouts instead
     // (and enough distinct minimizers: about 1 in 9 canonical m-mers ever is one)
-    const double local_load = cfg.bucket_load > 0 ? std::min(cfg.bucket_load, 3.5) : 2.5;
+    const double local_load = cfg.bucket_load > 0 ? std::min(cfg.bucket_load, 3.8) : 3.0;
     const double local_lines = (double)n_entries / (4.0 * local_load) * grow + 16;
     const bool local_fits = cfg.k >= LOCAL_MIN_K && cfg.k <= 32 &&
         (local_min_lines(cfg.k) * 128ull <= (8ull << 30) || (double)local_min_lines(cfg.k) <= 4.0 * local_lines) &&
@@ -428,8 +514,8 @@ Geometry choose_geometry(const cuclark_config& cfg, uint64_t n_entries, double g
         (double)local_min_lines(cfg.k) <= 1.25 * local_lines && 4.0 * local_lines < 4.2e9 && !getenv("CUCLARK_NO_LOCAL"))
         layout = LAYOUT_LOCAL;
     if (layout == LAYOUT_LOCAL && local_fits) {
-        // entries per 4-slot sector; the k-mers of a read that share a minimizer arrive in
-        // clumps of ~4.5 per line, so the load stays below that of the hashed layouts
+        // entries per 4-slot sector (two candidate lines per minimizer even out the clumps of ~4.5 k-mers
+        // that share one)
         uint64_t nl = (uint64_t)local_lines;
         nl = std::max(nl, local_min_lines(cfg.k)) | 1ull;
         g.layout = LAYOUT_LOCAL;
@@ -577,6 +663,8 @@ int finish_build(cuclark_db* db, const Geometry& g, BuildBuffers& b, BuildCtx& x
     db->view.NL = g.NL;
     db->view.magicNL = g.NL ? (uint64_t)((((__uint128_t)1) << 64) / g.NL) : 0;
     set_local_divmod(db->view);
+    db->view.line_lo = (uint32_t)(g.lo >> 2);
+    db->view.line_n = (uint32_t)(g.n_local >> 2);
     b.free_temp();
     return CUCLARK_OK;
 }
@@ -866,7 +954,7 @@ int table_build_synthetic(cuclark_db* db, uint32_t seed, uint32_t n_targets, uin
 namespace {
 
 constexpr char CACHE_MAGIC[8] = {'C', 'U', 'C', 'B', '2', 'T', 'B', 'L'};
-constexpr uint32_t CACHE_VERSION = 1;
+constexpr uint32_t CACHE_VERSION = 2;   // 2: LOCAL tables have two candidate lines per minimizer
 constexpr size_t CACHE_IO_BYTES = 64ull << 20;
 
 struct CacheHeader {                 // 192 bytes, little endian
@@ -1045,7 +1133,7 @@ int table_load(cuclark_db* db, const char* path, const char* src_base, int sfact
     db->view.M = h.M; db->view.magic = (uint64_t)((((__uint128_t)1) << 64) / h.M);
     db->view.lo = h.lo; db->view.n_local = h.n_local; db->view.n_ovf = h.n_ovf;
     db->view.layout = (int)h.layout; db->view.k = db->cfg.k;
-    if (h.layout == LAYOUT_LOCAL) { db->view.NL = h.M / 4; db->view.magicNL = (uint64_t)((((__uint128_t)1) << 64) / db->view.NL); set_local_divmod(db->view); }
+    if (h.layout == LAYOUT_LOCAL) { db->view.NL = h.M / 4; db->view.magicNL = (uint64_t)((((__uint128_t)1) << 64) / db->view.NL); set_local_divmod(db->view); db->view.line_lo = (uint32_t)(h.lo >> 2); db->view.line_n = (uint32_t)(h.n_local >> 2); }
     db->n_entries = h.n_entries; db->n_spilled = h.n_spilled; db->n_spill_buckets = h.n_spill_buckets;
     db->src_sfactor = (int)h.sfactor;
     for (int i = 0; i < 3; i++) db->src_bytes[i] = h.src_bytes[i];

@@ -53,6 +53,21 @@ extern "C" long shim_local_check(int k, uint64_t NL, long n, int* first_bad) {
         const uint32_t rest = local_rest(c, o_c, m);
         const uint64_t q = (uint64_t)local_key_lo(z / NL, rest) | ((uint64_t)local_key_hi(rest, o_c, f) << 32);
         if (q != key || (z % NL) * 4 + (uint64_t)(o_c & 3) != sec) { *first_bad = 4; return t; }
+        // second candidate line: inside the shard, never the A line itself, and invertible from (B line, key)
+        {
+            const uint64_t line_lo = (NL / 3), line_n64 = NL - line_lo - (NL / 5);        // a shard in the middle
+            uint64_t sa, sb, k2;
+            local_locate2(c, k, NL, line_lo, (uint32_t)line_n64, sa, sb, k2);
+            if (sa != sec || k2 != key) { *first_bad = 6; return t; }
+            const uint64_t la = sa >> 2;
+            if (la - line_lo < line_n64) {
+                const uint64_t lbn = sb >> 2;
+                if (lbn == la || lbn - line_lo >= line_n64 || (sb & 3) != (sa & 3)) { *first_bad = 7; return t; }
+                const uint64_t altkey = key | ((uint64_t)LOCAL_ALT_BIT << 32);
+                if (local_rebuild2(lbn, altkey, k, NL, line_lo, (uint32_t)line_n64) != c) { *first_bad = 8; return t; }
+                if (local_rebuild2(la, key, k, NL, line_lo, (uint32_t)line_n64) != c) { *first_bad = 9; return t; }
+            } else if (sb != sa) { *first_bad = 10; return t; }
+        }
         // the kernel's 32-bit divmod
         const int sh = 2 * m > 32 ? 2 * m - 32 : 0;
         const uint32_t m32 = (uint32_t)((((__uint128_t)1) << (32 + sh)) / NL);

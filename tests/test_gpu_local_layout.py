@@ -44,7 +44,7 @@ def small_k_case(k, n_targets, genome_len, seed):
     return targets, kmers, labels, dbtools.entries_to_arrays(kmers, labels, HTSIZE_LIGHT, kb), kb
 
 
-@pytest.mark.parametrize("k,load", [(21, 0.0), (21, 3.4), (19, 3.0), (24, 2.5)])
+@pytest.mark.parametrize("k,load", [(21, 0.0), (21, 3.8), (19, 3.7), (24, 3.5)])
 def test_local_spills_every_kmer_and_random(oracle, k, load):
     """Each DB k-mer (both strands) and random k-mers as single-k-mer reads; tight loads force spills."""
     T, G = 8, 40_000
@@ -59,8 +59,8 @@ def test_local_spills_every_kmer_and_random(oracle, k, load):
         g.load_arrays(sz, ky, lb)
         st = g.stats()
         assert st["layout"] == LOCAL and st["n_entries"] == kmers.size
-        if load:
-            assert st["n_spilled"] > 1000 and st["n_spill_buckets"] > 500
+        if load:            # with two candidate lines only a nearly full table spills
+            assert st["n_spilled"] > 100 and st["n_spill_buckets"] > 100
         gf, _ = g.classify(ptr, cont)
     got = np.where(gf[:, 2] > 0, gf[:, 1].astype(np.int32) - 1, -1)
     assert np.array_equal(got, expect)
@@ -116,7 +116,7 @@ def test_local_reads_with_ties_and_long_parts(oracle, k):
     long_codes = np.concatenate([targets[2][:3000], 3 - targets[3][::-1][:2500]])
     data += b">long\n" + bytes(b"ACGT"[c] for c in long_codes) + b"\n"
     ptr, cont, final, rows, lookups = oracle_expect(oracle, odb, k, data, T, 23)
-    for load in (0.0, 3.2):
+    for load in (0.0, 3.7):
         with CuClarkDB(k, T, htsize=HTSIZE_LIGHT, layout=LOCAL, bucket_load=load) as g:
             g.load_arrays(sz, ky, lb)
             assert g.stats()["layout"] == LOCAL
@@ -179,7 +179,7 @@ def test_local_synthetic_builder_and_cache(oracle, tmp_path, k, gap):
     data = synth.reads_fasta(codes)
     ptr, cont, final, rows, lookups = oracle_expect(oracle, odb, k, data, T, 23)
     path = str(tmp_path / "t.b200")
-    with CuClarkDB(k, T, htsize=HTSIZE_LIGHT, layout=LOCAL, bucket_load=2.5 if k == 21 else 0.0) as g:
+    with CuClarkDB(k, T, htsize=HTSIZE_LIGHT, layout=LOCAL, bucket_load=3.6 if k == 21 else 0.0) as g:
         g.build_synthetic(seed, T, G, light_gap=gap)
         st = g.stats()
         assert st["layout"] == LOCAL and st["n_entries"] == kmers.size
