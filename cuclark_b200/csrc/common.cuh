@@ -92,7 +92,11 @@ struct TableView {
 // bits, the swap puts each pair back in order.
 __host__ __device__ __forceinline__ uint64_t revcomp2(uint64_t x, int k) {
 #ifdef __CUDA_ARCH__
-    uint64_t r = __brevll(x);
+    // on the two 32-bit halves: reverse the bits (and the halves), swap the bits of every pair, complement
+    uint32_t rl = __brev((uint32_t)(x >> 32)), rh = __brev((uint32_t)x);
+    rl = ~(((rl >> 1) & 0x55555555u) | ((rl & 0x55555555u) << 1));
+    rh = ~(((rh >> 1) & 0x55555555u) | ((rh & 0x55555555u) << 1));
+    return (((uint64_t)rh << 32) | rl) >> (64 - 2 * k);
 #else
     uint64_t r = x;
     r = ((r >> 1) & 0x5555555555555555ull) | ((r & 0x5555555555555555ull) << 1);
@@ -101,9 +105,9 @@ __host__ __device__ __forceinline__ uint64_t revcomp2(uint64_t x, int k) {
     r = ((r >> 8) & 0x00FF00FF00FF00FFull) | ((r & 0x00FF00FF00FF00FFull) << 8);
     r = ((r >> 16) & 0x0000FFFF0000FFFFull) | ((r & 0x0000FFFF0000FFFFull) << 16);
     r = (r >> 32) | (r << 32);
-#endif
     r = ((r >> 1) & 0x5555555555555555ull) | ((r & 0x5555555555555555ull) << 1);
     return (~r) >> (64 - 2 * k);
+#endif
 }
 
 __host__ __device__ __forceinline__ uint64_t canonical(uint64_t x, int k) {
@@ -120,17 +124,16 @@ __device__ __forceinline__ void divmod_M(uint64_t c, uint64_t M, uint64_t magic,
 }
 
 // ---- LOCAL layout: minimizer-addressed lines ---------------------------------------
-// Invertible mixing of an nbits-wide value (24 <= nbits <= 50): xor-shifts by ceil(nbits/2) are
-// involutions, the multiplier is odd, so local_unmix() undoes it exactly.
+// Invertible mixing of an nbits-wide value (24 <= nbits <= 50): the xor-shift by ceil(nbits/2) is an
+// involution, the multiplier is odd, so local_unmix() undoes it exactly.
 constexpr uint64_t LOCAL_MUL = 0xD6E8FEB86659FD93ull;
 
 __host__ __device__ __forceinline__ uint64_t local_mix(uint64_t u, int nbits) {
+    // fold the upper half into the lower one, then multiply: the top bits of the product (the order of the
+    // m-mers) and its low bits (the line) both depend on every bit of u
     const uint64_t mask = (~0ull) >> (64 - nbits);
-    const int s = (nbits + 1) >> 1;
-    u ^= u >> s;
-    u = (u * LOCAL_MUL) & mask;
-    u ^= u >> s;
-    return u;
+    u ^= u >> ((nbits + 1) >> 1);
+    return (u * LOCAL_MUL) & mask;
 }
 __host__ __device__ __forceinline__ uint64_t inv_odd64(uint64_t a) {   // a * x == 1 mod 2^64
     uint64_t x = a;
@@ -139,10 +142,8 @@ __host__ __device__ __forceinline__ uint64_t inv_odd64(uint64_t a) {   // a * x 
 }
 __host__ __device__ __forceinline__ uint64_t local_unmix(uint64_t z, int nbits) {
     const uint64_t mask = (~0ull) >> (64 - nbits);
-    const int s = (nbits + 1) >> 1;
-    z ^= z >> s;
     z = (z * inv_odd64(LOCAL_MUL)) & mask;
-    z ^= z >> s;
+    z ^= z >> ((nbits + 1) >> 1);
     return z;
 }
 // order of the m-mers inside a k-mer: the top 24 bits of the mixed canonical m-mer
@@ -288,12 +289,11 @@ __device__ __forceinline__ uint32_t match_sector(const Sector& s, uint64_t key) 
         }
     } else if (LAYOUT == LAYOUT_LOCAL) {
         const uint32_t k32 = (uint32_t)key;
-        const uint32_t nehi = ~__vcmpeq4(s.w[6], (uint32_t)(key >> 32) * 0x01010101u);  // 0x00 where the high byte matches
-#pragma unroll
-        for (int i = 0; i < LOCAL_SLOTS; i++) {
-            const uint32_t lw = s.w[4 + (i >> 1)];
-            if (((s.w[i] ^ k32) | ((nehi >> (8 * i)) & 0xFFu)) == 0u) label = (i & 1) ? (lw >> 16) : (lw & 0xFFFFu);
-        }
+        const uint32_t H = s.w[6] ^ ((uint32_t)(key >> 32) * 0x01010101u);     // byte i is 0 iff the high byte of slot i matches
+        if (((s.w[0] ^ k32) | __byte_perm(H, 0, 0x4440)) == 0u) label = s.w[4] & 0xFFFFu;
+        if (((s.w[1] ^ k32) | __byte_perm(H, 0, 0x4441)) == 0u) label = s.w[4] >> 16;
+        if (((s.w[2] ^ k32) | __byte_perm(H, 0, 0x4442)) == 0u) label = s.w[5] & 0xFFFFu;
+        if (((s.w[3] ^ k32) | __byte_perm(H, 0, 0x4443)) == 0u) label = s.w[5] >> 16;
     } else {
 #pragma unroll
         for (int i = 0; i < WIDE_SLOTS; i++) {
