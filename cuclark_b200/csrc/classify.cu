@@ -66,6 +66,15 @@ __device__ __forceinline__ uint64_t shfl64(uint64_t v, int src) {
     return ((uint64_t)hi << 32) | lo;
 }
 
+// top 64 bits of the 128-bit value (hi:lo) << s, 0 <= s <= 62: the 32 nucleotides that start s/2 nucleotides into
+// word hi. Two 32-bit funnel shifts (which take the amount mod 32) over operands picked by s >= 32.
+__device__ __forceinline__ uint64_t window64(uint64_t hi, uint64_t lo, int s) {
+    const uint32_t h1 = (uint32_t)(hi >> 32), h0 = (uint32_t)hi, l1 = (uint32_t)(lo >> 32), l0 = (uint32_t)lo;
+    const bool big = s >= 32;
+    const uint32_t a = big ? h0 : h1, b = big ? l1 : h0, c = big ? l0 : l1;
+    return ((uint64_t)__funnelshift_l(b, a, s) << 32) | __funnelshift_l(c, b, s);
+}
+
 // leader-only insert of (label, n) into the warp's table; false if it is full
 __device__ __forceinline__ bool tab_add(uint32_t* tkey, uint32_t* tcnt, uint32_t label, uint32_t n) {
     uint32_t slot = (label * 0x9E3779B1u) >> 26;          // 6 bits
@@ -233,8 +242,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, LAYOUT == LAYOUT_LOCAL ?
                                     x = carry_x; rc = carry_rc; zs[R] = carry_z; oh = carry_oh;
                                 } else {
                                     const uint64_t hi = shfl64(W, i & 31), lo = shfl64(W, (i + 1) & 31);
-                                    x = lane ? ((hi << (2 * lane)) | (lo >> (64 - 2 * lane))) : hi;
-                                    x >>= kshift;
+                                    x = window64(hi, lo, 2 * lane) >> kshift;
                                     rc = revcomp2(x, k);
                                     // first m-mer of x and its reverse complement (= last m-mer of rc); the x of a
                                     // row past the 32 words has undefined low bits, which neither of the two touches
@@ -318,8 +326,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, LAYOUT == LAYOUT_LOCAL ?
                             for (int j = 0; j < ILP; j++) {
                                 const int i = r0 + j;
                                 const uint64_t hi = shfl64(W, i & 31), lo = shfl64(W, (i + 1) & 31);
-                                uint64_t x = lane ? ((hi << (2 * lane)) | (lo >> (64 - 2 * lane))) : hi;
-                                x >>= kshift;
+                                const uint64_t x = window64(hi, lo, 2 * lane) >> kshift;
                                 const bool valid = i < rounds && cb + 32 * i + lane < nk;
                                 uint64_t b;
                                 divmod_M(canonical(x, k), T.M, T.magic, q[j], b);

@@ -132,7 +132,7 @@ __host__ __device__ __forceinline__ uint64_t local_mix(uint64_t u, int nbits) {
     // fold the upper half into the lower one, then multiply: the top bits of the product (the order of the
     // m-mers) and its low bits (the line) both depend on every bit of u
     const uint64_t mask = (~0ull) >> (64 - nbits);
-    u ^= u >> ((nbits + 1) >> 1);
+    u ^= (uint32_t)(u >> ((nbits + 1) >> 1));       // the shifted value has at most 32 bits (nbits <= 64)
     return (u * LOCAL_MUL) & mask;
 }
 __host__ __device__ __forceinline__ uint64_t inv_odd64(uint64_t a) {   // a * x == 1 mod 2^64
