@@ -224,15 +224,16 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, LAYOUT == LAYOUT_LOCAL ?
                             // ---- minimizer of every k-mer of the ILP rows. Each lane hashes the FIRST m-mer of
                             // its position (rows r0..r0+ILP: the windows of the last row reach 7 positions
                             // into the next one); a windowed minimum over 8 consecutive positions by doubling
-                            // across lanes gives every k-mer its minimizer. Two minima are kept: leftmost
-                            // and rightmost position of the smallest hash, because "leftmost in the
-                            // canonical orientation" is the rightmost one of a read showing the reverse strand.
+                            // across lanes gives every k-mer its minimizer: the LEFTMOST smallest hash in read
+                            // orientation. Where the smallest hash occurs twice the canonical k-mer may have
+                            // its other home (rightmost): the table keeps such k-mers in the overflow table
+                            // and flags both homes (common.cuh, "TIES").
                             constexpr int NR = ILP + 1;
                             const int m = k - LOCAL_W + 1, mbits = 2 * m;
                             const uint64_t mmask = (~0ull) >> (64 - mbits);
                             uint64_t xs[ILP], rcs[ILP];
                             uint64_t zs[NR];                  // mixed canonical m-mer | (a < b) << 63 | (a > b) << 62
-                            uint32_t AL[NR], AR[NR];
+                            uint32_t AL[NR];
 #pragma unroll
                             for (int R = 0; R < NR; R++) {
                                 const int i = r0 + R;
@@ -256,7 +257,6 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, LAYOUT == LAYOUT_LOCAL ?
                                 if (R < ILP) { xs[R < ILP ? R : 0] = x; rcs[R < ILP ? R : 0] = rc; }
                                 if (R == NR - 1) { carry_x = x; carry_rc = rc; carry_z = zs[R]; carry_oh = oh; }
                                 AL[R] = (oh << 8) | (uint32_t)(32 * R + lane);
-                                AR[R] = (oh << 8) | (uint32_t)(255 - (32 * R + lane));
                             }
                             have_carry = true;
 #pragma unroll
@@ -264,18 +264,12 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, LAYOUT == LAYOUT_LOCAL ?
                                 const int sft = 1 << lvl;
                                 const int src = (lane + sft) & 31;
                                 const bool wrap = lane + sft >= 32;
-                                uint32_t TL[NR], TR[NR];
+                                uint32_t TL[NR];
 #pragma unroll
-                                for (int R = 0; R < NR; R++) {
-                                    TL[R] = __shfl_sync(0xFFFFFFFFu, AL[R], src);
-                                    TR[R] = __shfl_sync(0xFFFFFFFFu, AR[R], src);
-                                }
+                                for (int R = 0; R < NR; R++) TL[R] = __shfl_sync(0xFFFFFFFFu, AL[R], src);
 #pragma unroll
-                                for (int R = 0; R < NR; R++) {
-                                    // (lanes near 31 of the last row take wrapped values: nobody reads them)
+                                for (int R = 0; R < NR; R++)     // (lanes near 31 of the last row take wrapped values: nobody reads them)
                                     AL[R] = min(AL[R], (wrap && R + 1 < NR) ? TL[R + 1 < NR ? R + 1 : R] : TL[R]);
-                                    AR[R] = min(AR[R], (wrap && R + 1 < NR) ? TR[R + 1 < NR ? R + 1 : R] : TR[R]);
-                                }
                             }
 #pragma unroll
                             for (int j = 0; j < ILP; j++) {
@@ -284,7 +278,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, LAYOUT == LAYOUT_LOCAL ?
                                 const uint64_t x = xs[j], rc = rcs[j];
                                 const bool is_fwd = x <= rc;
                                 const uint64_t c = is_fwd ? x : rc;
-                                const uint32_t pos = is_fwd ? (AL[j] & 255u) : 255u - (AR[j] & 255u);   // 32 j + lane + offset
+                                const uint32_t pos = AL[j] & 255u;                            // 32 j + lane + offset
                                 const int src = (int)(pos & 31u);
                                 const uint64_t z0 = shfl64(zs[j], src), z1 = shfl64(zs[j + 1], src);
                                 const uint64_t zf = (pos >> 5) == (uint32_t)j ? z0 : z1;

@@ -187,23 +187,48 @@ __host__ __device__ __forceinline__ uint32_t local_key_hi(uint32_t rest, int o, 
 // the LEFTMOST such offset in c's own orientation on ties. Returns the global sector index
 // (line * 4 + (offset & 3)) and the 37-bit key. Reference form: the classify kernel computes
 // the same thing with a rolling window minimum across lanes.
-__host__ __device__ __forceinline__ void local_locate(uint64_t c, int k, uint64_t NL, uint64_t& sector, uint64_t& key) {
+//
+// TIES. The kernel takes the leftmost smallest hash in READ orientation, which is the rightmost one of the
+// canonical k-mer when the read shows the other strand. A k-mer whose smallest order hash occurs at more than
+// one offset (the same m-mer twice: low-complexity sequence; or two m-mers colliding in 24 bits) therefore has
+// two possible homes. Such k-mers are never stored in the lines: the builder puts them into the overflow table and
+// flags the sectors of BOTH homes, so whichever one a lookup computes, it finds the flags and goes to the overflow
+// table. local_locate_both() reports the second home (rightmost offset) and whether the k-mer is such a tie.
+__host__ __device__ __forceinline__ void local_home_at(uint64_t c, int m, uint64_t NL, int o, uint64_t& sector, uint64_t& key) {
+    bool fwd;
+    const uint64_t z = local_mix(local_mmer(c, o, m, fwd), 2 * m);
+    const uint64_t line = z % NL, zq = z / NL;
+    const uint32_t rest = local_rest(c, o, m);
+    sector = line * 4 + (uint64_t)(o & 3);
+    key = (uint64_t)local_key_lo(zq, rest) | ((uint64_t)local_key_hi(rest, o, fwd) << 32);
+}
+__host__ __device__ __forceinline__ bool local_min_offsets(uint64_t c, int k, int& o_left, int& o_right) {
     const int m = k - LOCAL_W + 1;
     uint32_t best = 0xFFFFFFFFu;
-    int bo = 0;
-    bool bf = true;
-    uint64_t bz = 0;
+    o_left = o_right = 0;
     for (int o = 0; o < LOCAL_W; o++) {
         bool fwd;
-        const uint64_t z = local_mix(local_mmer(c, o, m, fwd), 2 * m);
-        const uint32_t h = local_order(z, 2 * m);
-        if (h < best) { best = h; bo = o; bf = fwd; bz = z; }
+        const uint32_t h = local_order(local_mix(local_mmer(c, o, m, fwd), 2 * m), 2 * m);
+        if (h < best) { best = h; o_left = o_right = o; }
+        else if (h == best) o_right = o;
     }
-    const uint64_t line = bz % NL, zq = bz / NL;
-    const uint32_t rest = local_rest(c, bo, m);
-    sector = line * 4 + (uint64_t)(bo & 3);
-    key = (uint64_t)local_key_lo(zq, rest) | ((uint64_t)local_key_hi(rest, bo, bf) << 32);
+    return o_left != o_right;
 }
+__host__ __device__ __forceinline__ void local_locate(uint64_t c, int k, uint64_t NL, uint64_t& sector, uint64_t& key) {
+    int ol, orr;
+    local_min_offsets(c, k, ol, orr);
+    local_home_at(c, k - LOCAL_W + 1, NL, ol, sector, key);
+}
+__host__ __device__ __forceinline__ bool local_locate_both(uint64_t c, int k, uint64_t NL, uint64_t& sec_l, uint64_t& key_l,
+                                                           uint64_t& sec_r, uint64_t& key_r) {
+    int ol, orr;
+    const bool tie = local_min_offsets(c, k, ol, orr);
+    local_home_at(c, k - LOCAL_W + 1, NL, ol, sec_l, key_l);
+    local_home_at(c, k - LOCAL_W + 1, NL, orr, sec_r, key_r);
+    return tie;
+}
+// B sector (global index) of a home whose A sector is sec_a; sec_a itself when the A line is outside the shard
+__host__ __device__ __forceinline__ uint64_t local_alt_sector(uint64_t sec_a, uint64_t key, uint64_t line_lo, uint32_t line_n);
 // ---- second candidate line -----------------------------------------------------------
 constexpr uint32_t LOCAL_ALT_BIT = 1u << 5;            // in the key's high byte: the entry lives in its B line
 // distance from a k-mer's A line to its B line, inside its shard's nloc lines; a function of the part of
@@ -223,6 +248,11 @@ __host__ __device__ __forceinline__ uint64_t local_alt_line(uint64_t line_a, uin
     if (rel >= line_n) rel -= line_n;
     return line_lo + rel;
 }
+__host__ __device__ __forceinline__ uint64_t local_alt_sector(uint64_t sec_a, uint64_t key, uint64_t line_lo, uint32_t line_n) {
+    const uint64_t line_a = sec_a >> 2;
+    if (line_a - line_lo >= line_n) return sec_a;
+    return local_alt_line(line_a, (uint32_t)(key & ((1ull << LOCAL_ZQ_BITS) - 1)), line_lo, line_n) * 4 + (sec_a & 3);
+}
 __host__ __device__ __forceinline__ uint64_t local_alt_line_inv(uint64_t line_b, uint32_t zq, uint64_t line_lo, uint32_t line_n) {
     const uint32_t step = local_alt_step(zq, line_n);
     uint64_t rel = line_b - line_lo;
@@ -233,10 +263,7 @@ __host__ __device__ __forceinline__ uint64_t local_alt_line_inv(uint64_t line_b,
 __host__ __device__ __forceinline__ void local_locate2(uint64_t c, int k, uint64_t NL, uint64_t line_lo, uint32_t line_n,
                                                        uint64_t& sec_a, uint64_t& sec_b, uint64_t& key) {
     local_locate(c, k, NL, sec_a, key);
-    const uint64_t line_a = sec_a >> 2;
-    sec_b = sec_a;
-    if (line_a - line_lo < line_n)
-        sec_b = local_alt_line(line_a, (uint32_t)(key & ((1ull << LOCAL_ZQ_BITS) - 1)), line_lo, line_n) * 4 + (sec_a & 3);
+    sec_b = local_alt_sector(sec_a, key, line_lo, line_n);
 }
 // the k-mer stored as `key` (with or without LOCAL_ALT_BIT) in a sector of global line `line`
 __host__ __device__ __forceinline__ uint64_t local_rebuild(uint64_t line, uint64_t key, int k, uint64_t NL);

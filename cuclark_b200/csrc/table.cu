@@ -91,8 +91,20 @@ __device__ __forceinline__ bool insert_home(const BuildCtx& x, uint64_t c, uint3
     if (LAYOUT == LAYOUT_LOCAL) {
         // two candidate sectors (A line, B line): take the emptier one, the other if that one fills up
         // under our feet; the overflow table only when both are full
-        uint64_t sa, sb;
-        local_locate2(c, x.k, x.NL, x.lo >> 2, (uint32_t)(x.n_local >> 2), sa, sb, q);
+        uint64_t sa, sb, sr, qr;
+        const bool tie = local_locate_both(c, x.k, x.NL, sa, q, sr, qr);
+        if (tie) {
+            // two possible homes (common.cuh, "TIES"): lives in the overflow table of every shard that holds one of
+            // them (k_place_spills flags their sectors); counted by the shard of the first home
+            const bool mine = sa - x.lo < x.n_local;
+            if (mine || sr - x.lo < x.n_local) {
+                const uint32_t i = atomicAdd(&x.flags[0], 1u);
+                if (i < x.ovf_cap) { x.ovf_c[i] = c; x.ovf_l[i] = (uint16_t)label; }
+                else atomicOr(&x.flags[1], ERR_OVF_LIST);
+            }
+            return mine;
+        }
+        sb = local_alt_sector(sa, q, x.lo >> 2, (uint32_t)(x.n_local >> 2));
         const uint64_t la = sa - x.lo, lbb = sb - x.lo;
         if (la >= x.n_local) return false;           // homed in another shard
         const uint32_t ca = (__ldcg(&x.cnt8[la >> 2]) >> (8 * (uint32_t)(la & 3))) & 0xFFu;
@@ -194,15 +206,20 @@ __global__ void k_place_spills(BuildCtx x, uint32_t n) {
     const uint64_t c = x.ovf_c[i];
     const uint32_t label = x.ovf_l[i];
     uint64_t q, b;
-    if (x.layout == LAYOUT_LOCAL) {                  // both candidate sectors were full
-        uint64_t sb;
-        local_locate2(c, x.k, x.NL, x.lo >> 2, (uint32_t)(x.n_local >> 2), b, sb, q);
-        atomicOr(reinterpret_cast<uint32_t*>(x.table + 2 * (sb - x.lo)) + 7, 1u << 16);
+    if (x.layout == LAYOUT_LOCAL) {
+        // both candidate sectors were full, or a tie k-mer: flag the A and B sector of its home(s) held by this shard
+        uint64_t sec[2], key[2];
+        const bool tie = local_locate_both(c, x.k, x.NL, sec[0], key[0], sec[1], key[1]);
+        for (int h = 0; h < (tie ? 2 : 1); h++) {
+            if (sec[h] - x.lo >= x.n_local) continue;
+            const uint64_t sb = local_alt_sector(sec[h], key[h], x.lo >> 2, (uint32_t)(x.n_local >> 2));
+            atomicOr(reinterpret_cast<uint32_t*>(x.table + 2 * (sec[h] - x.lo)) + 7, 1u << 16);
+            atomicOr(reinterpret_cast<uint32_t*>(x.table + 2 * (sb - x.lo)) + 7, 1u << 16);
+        }
     } else {
         home_of_rt(x.layout, c, x.M, x.magic, x.NL, x.k, q, b);
+        atomicOr(reinterpret_cast<uint32_t*>(x.table + 2 * (b - x.lo)) + 7, 1u << 16);
     }
-    const uint64_t lb = b - x.lo;
-    atomicOr(reinterpret_cast<uint32_t*>(x.table + 2 * lb) + 7, 1u << 16);
     uint64_t ob = ovf_home(c, x.n_ovf);
     for (uint64_t n_try = 0; n_try < x.n_ovf; n_try++) {
         // the counter saturates logically at WIDE_SLOTS; do not wrap its byte
@@ -416,8 +433,8 @@ __global__ void k_dedupe_ovf(DedupeView<LAYOUT> v, uint64_t magic) {
         if (LAYOUT == LAYOUT_LOCAL) {               // copies in the two candidate sectors
             uint64_t sa, sb, q;
             local_locate2(c, v.k, v.NL, v.lo >> 2, (uint32_t)(v.n_local >> 2), sa, sb, q);
-            bool in_main;
-            local_main_copies(v.table, sa - v.lo, sb - v.lo, q, label, ~0ull, 0, differ, in_main);
+            bool in_main = false;                   // (tie k-mers never have copies in the lines)
+            if (sa - v.lo < v.n_local) local_main_copies(v.table, sa - v.lo, sb - v.lo, q, label, ~0ull, 0, differ, in_main);
             if (differ || in_main || before) del |= 1u << s;
             continue;
         }

@@ -36,6 +36,7 @@ extern "C" long shim_local_check(int k, uint64_t NL, long n, int* first_bad) {
         local_locate(c, k, NL, sec, key);
         if (key >> 37) { *first_bad = 1; return t; }
         if (local_rebuild(sec >> 2, key, k, NL) != c) { *first_bad = 2; return t; }
+        // the kernel: leftmost smallest hash in READ orientation
         uint32_t best = 0xFFFFFFFFu;
         int offL = 0, offR = 0;
         for (int o = 0; o < LOCAL_W; o++) {
@@ -43,8 +44,7 @@ extern "C" long shim_local_check(int k, uint64_t NL, long n, int* first_bad) {
             const uint32_t h = local_order(local_mix(a < b ? a : b, 2 * m), 2 * m);
             if (h < best) { best = h; offL = offR = o; } else if (h == best) offR = o;
         }
-        ties += offL != offR;
-        const int o_read = is_fwd ? offL : offR;
+        const int o_read = offL;
         const uint64_t a = (x >> (2 * (LOCAL_W - 1 - o_read))) & mmask, b = revcomp2(a, m);
         const uint64_t z = local_mix(a < b ? a : b, 2 * m);
         if (local_unmix(z, 2 * m) != (a < b ? a : b)) { *first_bad = 3; return t; }
@@ -52,7 +52,17 @@ extern "C" long shim_local_check(int k, uint64_t NL, long n, int* first_bad) {
         const bool f = is_fwd ? a < b : a > b;
         const uint32_t rest = local_rest(c, o_c, m);
         const uint64_t q = (uint64_t)local_key_lo(z / NL, rest) | ((uint64_t)local_key_hi(rest, o_c, f) << 32);
-        if (q != key || (z % NL) * 4 + (uint64_t)(o_c & 3) != sec) { *first_bad = 4; return t; }
+        const uint64_t qsec = (z % NL) * 4 + (uint64_t)(o_c & 3);
+        // the builder: one home, or two for a tie (then the k-mer lives in the overflow table and both homes are flagged)
+        uint64_t sl, kl, sr, kr;
+        const bool tie = local_locate_both(c, k, NL, sl, kl, sr, kr);
+        if (tie != (offL != offR)) { *first_bad = 11; return t; }
+        if (sl != sec || kl != key) { *first_bad = 12; return t; }
+        ties += tie;
+        if (!tie) {
+            if (q != key || qsec != sec) { *first_bad = 4; return t; }
+        } else if (!((q == kl && qsec == sl) || (q == kr && qsec == sr))) { *first_bad = 13; return t; }
+        if (local_rebuild(qsec >> 2, q, k, NL) != c) { *first_bad = 14; return t; }
         // second candidate line: inside the shard, never the A line itself, and invertible from (B line, key)
         {
             const uint64_t line_lo = (NL / 3), line_n64 = NL - line_lo - (NL / 5);        // a shard in the middle
