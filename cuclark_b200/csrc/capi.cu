@@ -110,6 +110,10 @@ int cuclark_create(const cuclark_config* cfg, cuclark_db** out) {
     cuclark_db* db = new cuclark_db();
     db->cfg = *cfg;
     if (db->cfg.shard_count < 1) { db->cfg.shard_count = 1; db->cfg.shard_index = 0; }
+    if (db->cfg.layout == 0) {                        // CUCLARK_LAYOUT=1|2|3 forces a table layout for handles that left it open
+        const char* e = getenv("CUCLARK_LAYOUT");     // (the command line has no flag for it)
+        if (e && e[0] >= '1' && e[0] <= '3' && !e[1]) db->cfg.layout = e[0] - '0';
+    }
     db->key_bytes = cfg->key_bytes ? cfg->key_bytes : key_bytes_for(cfg->k, cfg->htsize);
     db->row_pairs = cfg->row_pairs > 0 ? cfg->row_pairs
                                        : (cfg->htsize == CUCLARK_HTSIZE_LIGHT ? CUCLARK_MAXHITS_LIGHT : CUCLARK_MAXHITS_FULL);

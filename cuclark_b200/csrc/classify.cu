@@ -6,9 +6,13 @@
 //   * lane j keeps 32 nucleotides of the current part as one 64-bit word; a
 //     k-mer is a funnel shift of two neighbouring words fetched by shuffle
 //     (no shared-memory staging, no per-thread re-assembly);
-//   * canonical k-mer -> (home bucket, exact quotient) -> ONE 256-bit load of
-//     the 32-byte sector bucket; ILP_ROUNDS independent probes per lane are in
+//   * hashed tables: canonical k-mer -> (home bucket, exact quotient) -> ONE 256-bit
+//     load of the 32-byte sector bucket; ILP_ROUNDS independent probes per lane are in
 //     flight before any is consumed;
+//   * LOCAL tables (common.cuh): the home is chosen by the k-mer's canonical minimizer
+//     (rolling window minimum of m-mer hashes across lanes), so the ~4.5 consecutive
+//     k-mers that share one probe the same two 128-byte lines and adjacent lanes
+//     coalesce; 1.5x the lookups of the hashed kernel, bound by the integer ALU pipe;
 //   * per-read target counts live in a 64-slot per-warp hash table in shared
 //     memory (the reference zeroes and scans numTargets counters per read), with
 //     a register fast path while a read has hit a single target;

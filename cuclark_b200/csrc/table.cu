@@ -395,9 +395,7 @@ __global__ void k_dedupe_main(DedupeView<LAYOUT> v) {
             }
             if (differ || earlier) del |= 1u << i;  // main copies precede overflow copies
         }
-        v.del_main[lb] = (uint8_t)del;
-        return;
-    }
+    } else {
     for (int i = 0; i < SLOTS; i++) {
         if (!used[i]) continue;
         bool differ = false, earlier = false;
@@ -412,6 +410,7 @@ __global__ void k_dedupe_main(DedupeView<LAYOUT> v) {
             ovf_scan(v.ovf, v.n_ovf, c, labels[i], ~0ull, 0, differ, total);
         }
         if (differ || earlier) del |= 1u << i;      // main copies precede overflow copies
+    }
     }
     v.del_main[lb] = (uint8_t)del;
 }
@@ -911,8 +910,8 @@ int table_build_from_arrays(cuclark_db* db, const uint8_t* sz_in, const void* ky
     }
     if (timing)
         fprintf(stderr, "[cuclark timing] database load: host pass over %llu bucket sizes %.1f ms on %d threads, "
-                        "upload + device re-bucketing of %llu entries %.1f ms\n",
-                (unsigned long long)H, ms_scan, n_thr, (unsigned long long)kept, since(t_build));
+                        "upload + device re-bucketing of %llu entries %.1f ms (table layout %d)\n",
+                (unsigned long long)H, ms_scan, n_thr, (unsigned long long)kept, since(t_build), db->view.layout);
     return rc;
 }
 

@@ -121,6 +121,26 @@ def test_cli_light_fasta_equals_reference_csv(exes, light_small, tmp_path):
 
 
 @pytest.mark.gpu
+def test_cli_through_the_local_table_layout(exes, light_small, tmp_path):
+    """The same command line with the table in the LOCAL layout (minimizer-addressed lines; chosen automatically
+    only at bacterial scale, forced here through CUCLARK_LAYOUT): byte-identical CSVs, plain and --extended."""
+    reads = setup_case(light_small, str(tmp_path))
+    env = dict(os.environ, CUCLARK_LAYOUT="3", CUCLARK_TIMING="1")
+    p = subprocess.run([exes[1], "-T", "targets.txt", "-D", "db/", "-O", os.path.basename(reads), "-R", "out", "-n", "2"],
+                       cwd=str(tmp_path), capture_output=True, text=True, env=env)
+    assert p.returncode == 0, p.stderr
+    ref = gzip.open(os.path.join(GOLDEN, "light_small.csv.gz")).read()
+    assert (tmp_path / "out.csv").read_bytes() == ref
+    assert "(table layout 3)" in p.stderr
+    p1 = subprocess.run([exes[1], "-T", "targets.txt", "-D", "db/", "-O", "reads.fa", "-R", "ext_local", "--extended"],
+                        cwd=str(tmp_path), capture_output=True, text=True, env=env)
+    p2 = subprocess.run([exes[1], "-T", "targets.txt", "-D", "db/", "-O", "reads.fa", "-R", "ext_hashed", "--extended"],
+                        cwd=str(tmp_path), capture_output=True, text=True, env=dict(os.environ, CUCLARK_LAYOUT="1"))
+    assert p1.returncode == 0 and p2.returncode == 0, p1.stderr + p2.stderr
+    assert (tmp_path / "ext_local.csv").read_bytes() == (tmp_path / "ext_hashed.csv").read_bytes()
+
+
+@pytest.mark.gpu
 def test_cli_extended_equals_oracle(exes, oracle, light_small, tmp_path):
     c = light_small
     reads = setup_case(c, str(tmp_path))
