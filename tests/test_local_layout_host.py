@@ -33,7 +33,7 @@ def shim(tmp_path_factory):
 def test_locate_rebuild_and_kernel_route(shim, k):
     m = k - 8 + 1
     min_lines = 1 << max(0, 2 * m - 19)          # key width: mix(minimizer) div NL must fit 19 bits
-    for nl in (max(min_lines, 1000) | 1, (max(min_lines, 1000) * 3 // 2) | 1):
+    for nl in (max(min_lines, 1024), max(min_lines, 1000) | 1, (max(min_lines, 1000) * 3 // 2) | 1):   # power of two, odd, odd
         bad = C.c_int(-1)
         ties = shim.shim_local_check(k, nl, 300_000, C.byref(bad))
         assert bad.value == 0, f"k={k} NL={nl}: check {bad.value} failed at k-mer #{ties}"
