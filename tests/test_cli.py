@@ -196,6 +196,53 @@ def test_cli_paired_end(exes, oracle, light_small, tmp_path):
 
 @pytest.mark.gpu
 @pytest.mark.slow
+def test_cli_config3_paired_k31_with_errors(exes, oracle, full_small, tmp_path):
+    """BASELINE configs[2] in small: cuCLARK k=31, paired-end 2 x 150 bp, mate 2 from the opposite strand, 1 %
+    substitution errors; mates merged by the reference rule, Length 300, gamma over 300-31+1 (paired-mode voting)."""
+    c = full_small
+    setup_case(c, str(tmp_path), write_reads=False)
+    import sys
+    asc = np.frombuffer(b"ACGT", np.uint8)
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+    mg = sys.modules["make_golden"]
+    rng = np.random.default_rng(31)
+    genomes = [asc[mg.target_codes(c.case, t)].tobytes() for t in range(c.n_targets)]
+
+    def with_errors(seq: bytes) -> bytes:
+        b = bytearray(seq)
+        for j in np.nonzero(rng.random(len(b)) < 0.01)[0]:
+            b[j] = b"ACGT"[(b"ACGT".index(b[j]) + 1 + int(rng.integers(0, 3))) % 4]
+        return bytes(b)
+
+    f1, f2 = [], []
+    for i in range(4000):
+        g = genomes[int(rng.integers(0, c.n_targets))]
+        pos = int(rng.integers(0, len(g) - 600))
+        s1 = with_errors(g[pos:pos + 150])
+        s2 = with_errors(g[pos + 350:pos + 500].translate(comp)[::-1])
+        f1.append(b"@frag%d/1\n%s\n+\n%s\n" % (i, s1, b"F" * 150))
+        f2.append(b"@frag%d/2\n%s\n+\n%s\n" % (i, s2, b"F" * 150))
+    (tmp_path / "r1.fq").write_bytes(b"".join(f1))
+    (tmp_path / "r2.fq").write_bytes(b"".join(f2))
+    assert oracle.merge_paired(str(tmp_path / "r1.fq"), str(tmp_path / "r2.fq"), str(tmp_path / "merged.fa")) == 0
+    merged = (tmp_path / "merged.fa").read_bytes()
+    sz, ky, lb = c.arrays
+    odb = oracle.db_from_arrays(c.htsize, c.k, sz, ky, lb)
+    ix, buf = oracle.index(merged, 1)
+    ptr, cont = oracle.pack(ix, buf, c.k)
+    final, rows, _ = oracle.classify(odb, ptr, cont, c.n_targets, c.maxhits, threads=4)
+    oracle.write_csv(str(tmp_path / "oracle.csv"), ix, buf, c.k, True, c.names, final, None, c.maxhits)
+    oracle.free_index(ix)
+    p = run([exes[0], "-k", "31", "-T", "targets.txt", "-D", "db/", "-P", "r1.fq", "r2.fq", "-R", "paired"], cwd=str(tmp_path))
+    assert p.returncode == 0, p.stderr
+    got = (tmp_path / "paired.csv").read_bytes()
+    assert got == (tmp_path / "oracle.csv").read_bytes()
+    assert got.split(b"\n")[1].startswith(b"frag0,300,")
+    assert (final[:, 1] > 0).mean() > 0.95 and (final[:, 0] < 2 * (150 - 31 + 1)).mean() > 0.9    # classified, but errors cost k-mers
+
+
+@pytest.mark.gpu
+@pytest.mark.slow
 def test_cli_full_fastq_equals_reference_csv(exes, full_small, tmp_path):
     reads = setup_case(full_small, str(tmp_path))
     p = run([exes[0], "-k", "31", "-T", "targets.txt", "-D", "db/", "-O", os.path.basename(reads), "-R", "out"],
