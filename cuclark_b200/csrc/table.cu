@@ -523,7 +523,8 @@ Geometry choose_geometry(const cuclark_config& cfg, uint64_t n_entries, double g
     const double local_lines = (double)n_entries / (4.0 * local_load) * grow + 16;
     const bool local_fits = cfg.k >= LOCAL_MIN_K && cfg.k <= 32 &&
         (local_min_lines(cfg.k) * 128ull <= (8ull << 30) || (double)local_min_lines(cfg.k) <= 4.0 * local_lines) &&
-        (double)pow4(cfg.k - LOCAL_W + 1) / 9.0 >= 4.0 * local_lines;
+        (double)pow4(cfg.k - LOCAL_W + 1) / 9.0 >= 4.0 * local_lines &&
+        local_lines < 1.0e9 && (double)local_min_lines(cfg.k) < 1.0e9;     // 4 NL < 2^32 sectors, 3 NL < 2^32 (local_divmod)
     // automatic choice: minimizer lines for a single-device table that fills them (at bacterial scale they
     // serve ~1.25x the lookups of the hashed sectors; a small database would pay the minimum size for nothing)
     if (layout == 0 && allow_auto_local && cfg.shard_count <= 1 && local_fits && cfg.bucket_load <= 0 &&
