@@ -68,8 +68,10 @@ typedef struct cuclark_config {
     double bucket_load;   /* mean entries per 32-byte bucket; 0 = default                    */
     int layout;           /* 0 auto, 1 narrow (5 x 32-bit key), 2 wide (3 x 64-bit key),     */
                           /* 3 local (minimizer-addressed 128-byte lines of 4 x 4 37-bit     */
-                          /* keys; k >= 19 and a table of at least 4^(k-7)/2^19 lines; auto  */
-                          /* takes it for single-device tables that fill that minimum)       */
+                          /* keys, two candidate lines per minimizer; k >= 19 and a table of */
+                          /* at least 4^(k-7)/2^19 lines; auto takes it for single-device    */
+                          /* tables that fill that minimum; env CUCLARK_LAYOUT=1|2|3 decides */
+                          /* for handles that pass 0, CUCLARK_NO_LOCAL=1 keeps auto hashed)  */
 } cuclark_config;
 
 typedef struct cuclark_stats {
