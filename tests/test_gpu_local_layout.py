@@ -193,3 +193,64 @@ def test_local_synthetic_builder_and_cache(oracle, tmp_path, k, gap):
             assert st2[key] == st[key], key
         gf2, gr2 = g2.classify(ptr, cont, want_rows=True)
     assert np.array_equal(gf2, final) and np.array_equal(gr2, rows)
+
+
+def test_local_many_targets_dense_fallback(oracle):
+    """> 64 distinct targets in one read: the exact dense fallback probes the LOCAL table through table_lookup()
+    (brute-force minimizer, both candidate sectors, overflow table), at a load that spills entries."""
+    k, T, G = 27, 300, 2000
+    targets = [synth.genome_codes(77, t, 0, G) for t in range(T)]
+    kmers, labels = dbtools.build_entries(targets, k, 0)
+    sz, ky, lb = dbtools.entries_to_arrays(kmers, labels, HTSIZE_LIGHT, 4)
+    odb = oracle.db_from_arrays(HTSIZE_LIGHT, k, sz, ky, lb)
+    asc = np.frombuffer(b"ACGT", np.uint8)
+    seg = lambda t, n: asc[targets[t][100:100 + n]].tobytes()
+    reads = [
+        b">r70\n" + b"".join(seg(t, 40) for t in range(0, 70)) + b"\n",
+        b">r200\n" + b"".join(seg(t, 30 + (t % 7)) for t in range(299, 99, -1)) + b"\n",
+        b">r64\n" + b"".join(seg(t, 40) for t in range(100, 164)) + b"\n",
+        b">r20\n" + b"".join(seg(t, 45) for t in range(10, 30)) + b"\n",
+        b">r1\n" + seg(5, 200) + b"\n",
+    ]
+    data = b"".join(reads)
+    ptr, cont, final, rows, _ = oracle_expect(oracle, odb, k, data, T, 23)
+    for load in (0.0, 3.7):
+        with CuClarkDB(k, T, htsize=HTSIZE_LIGHT, row_pairs=23, layout=LOCAL, bucket_load=load) as g:
+            g.load_arrays(sz, ky, lb)
+            gf, gr = g.classify(ptr, cont, want_rows=True)
+            st = g.stats()
+        assert st["layout"] == LOCAL and st["dense_reads"] == 2
+        assert np.array_equal(gf, final) and np.array_equal(gr, rows)
+
+
+@pytest.mark.parametrize("sfactor", [2, 5])
+def test_local_sampling_factor_and_batches(oracle, light_small, sfactor):
+    """-s sampling at load time and the CuClarkDB batch API (malloc / readyBatch / queryBatch / waitForBatch) on a LOCAL table."""
+    c = light_small
+    sz, ky, lb = c.arrays
+    odb = oracle.db_from_arrays(c.htsize, c.k, sz, ky, lb, sfactor=sfactor)
+    ptr, cont, final, rows, _ = oracle_expect(oracle, odb, c.k, c.reads_bytes, c.n_targets, c.maxhits)
+    n = ptr.size - 1
+    with CuClarkDB(c.k, c.n_targets, htsize=c.htsize, layout=LOCAL) as g:
+        g.load_arrays(sz, ky, lb, mod_collision=sfactor)
+        assert g.stats()["layout"] == LOCAL and g.stats()["n_entries"] == odb.size
+        gf, gr = g.classify(ptr, cont, want_rows=True)
+        assert np.array_equal(gf, final) and np.array_equal(gr, rows)
+        nb = 3
+        bounds = [n * b // nb for b in range(nb + 1)]
+        max_reads = max(bounds[b + 1] - bounds[b] for b in range(nb))
+        max_cont = max(int(ptr[bounds[b + 1]] - ptr[bounds[b]]) for b in range(nb))
+        views = g.malloc(nb, max_reads, max_cont, is_extended=True)
+        for b in range(nb):
+            lo, hi = bounds[b], bounds[b + 1]
+            vp, vc, _, _ = views[b]
+            vp[:hi - lo + 1] = ptr[lo:hi + 1] - ptr[lo]
+            vc[:int(ptr[hi] - ptr[lo])] = cont[ptr[lo]:ptr[hi]]
+            g.readyBatch(b, hi - lo, int(ptr[hi] - ptr[lo]))
+            g.queryBatch(b, True)
+        for b in range(nb):
+            g.waitForBatch(b)
+            lo, hi = bounds[b], bounds[b + 1]
+            assert np.array_equal(views[b][2][:hi - lo], final[lo:hi])
+            assert np.array_equal(views[b][3][:hi - lo], rows[lo:hi])
+        g.freeBatchMemory()
