@@ -300,8 +300,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, LAYOUT == LAYOUT_LOCAL ?
                                 lb[j] = (uint32_t)lb64;
                                 live[j] = valid && lb64 < T.n_local;
                                 my_lookups += valid;
-                                uint32_t rel_b = line - T.line_lo + local_alt_step(zq, T.line_n);
-                                if (rel_b >= T.line_n) rel_b -= T.line_n;
+                                const uint32_t rel_b = local_alt_rel(line - T.line_lo, zq, T.line_n, false);
                                 if (live[j]) {
                                     sec[j] = load_sector_line(T.buckets + 2 * (uint64_t)lb[j]);
                                     secb[j] = load_sector_line(T.buckets + 2 * ((uint64_t)rel_b * 4 + (uint64_t)(o_c & 3)));

@@ -231,33 +231,44 @@ __host__ __device__ __forceinline__ bool local_locate_both(uint64_t c, int k, ui
 __host__ __device__ __forceinline__ uint64_t local_alt_sector(uint64_t sec_a, uint64_t key, uint64_t line_lo, uint32_t line_n);
 // ---- second candidate line -----------------------------------------------------------
 constexpr uint32_t LOCAL_ALT_BIT = 1u << 5;            // in the key's high byte: the entry lives in its B line
-// distance from a k-mer's A line to its B line, inside its shard's nloc lines; a function of the part of
-// the mixed minimizer that the key keeps (zq), so that the A line is recoverable from (B line, key)
-__host__ __device__ __forceinline__ uint32_t local_alt_step(uint32_t zq, uint32_t nloc) {
-    if (nloc < 2) return 0;
-    const uint32_t h = zq * 0x9E3779B1u + 0x7F4A7C15u;
-#ifdef __CUDA_ARCH__
-    return 1u + __umulhi(h, nloc - 1u);
-#else
-    return 1u + (uint32_t)(((uint64_t)h * (nloc - 1u)) >> 32);
+// The B line is the A line rotated inside its block of LOCAL_ALT_BLOCK lines by a step that is a function of the part of the mixed
+// minimizer the key keeps (zq), so that the A line is recoverable from (B line, key).
+// The block is 256 lines = 32 KB: measured on an 8 G-entry table (96 GB, past the reach of the TLBs) 38 G lookups/s with
+// the B line anywhere in the table, 46 with it in the same 2 MB page, 53 within 128 KB, 58 within 32 KB or 16 KB; the
+// smaller the block the less even the fill (overflowed entries 4.87 % -> 4.91 % at 32 KB, 5.2 % at 4 KB).
+#ifndef CUCLARK_ALT_BLOCK_LINES
+#define CUCLARK_ALT_BLOCK_LINES 256
 #endif
+constexpr uint32_t LOCAL_ALT_BLOCK = CUCLARK_ALT_BLOCK_LINES;   // power of two
+__host__ __device__ __forceinline__ uint32_t local_mulhi32(uint32_t a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * b) >> 32);
+#endif
+}
+// A line -> B line (inverse = false) or B line -> A line (inverse = true), as indices relative to the shard's
+// first line: a rotation by step(zq) inside the block of the line (the last block may be shorter)
+__host__ __device__ __forceinline__ uint32_t local_alt_rel(uint32_t rel, uint32_t zq, uint32_t line_n, bool inverse) {
+    const uint32_t start = rel & ~(LOCAL_ALT_BLOCK - 1u);
+    const uint32_t size = line_n - start < LOCAL_ALT_BLOCK ? line_n - start : LOCAL_ALT_BLOCK;
+    if (size < 2) return rel;
+    const uint32_t step = 1u + local_mulhi32(zq * 0x9E3779B1u + 0x7F4A7C15u, size - 1u);     // 1 .. size-1
+    uint32_t off = rel - start;
+    off = inverse ? (off >= step ? off - step : off + size - step) : (off + step >= size ? off + step - size : off + step);
+    return start + off;
 }
 // B line (global index) of the k-mer with A line `line_a` and key part zq; shard lines [line_lo, line_lo + line_n)
 __host__ __device__ __forceinline__ uint64_t local_alt_line(uint64_t line_a, uint32_t zq, uint64_t line_lo, uint32_t line_n) {
-    uint64_t rel = line_a - line_lo + local_alt_step(zq, line_n);
-    if (rel >= line_n) rel -= line_n;
-    return line_lo + rel;
+    return line_lo + local_alt_rel((uint32_t)(line_a - line_lo), zq, line_n, false);
+}
+__host__ __device__ __forceinline__ uint64_t local_alt_line_inv(uint64_t line_b, uint32_t zq, uint64_t line_lo, uint32_t line_n) {
+    return line_lo + local_alt_rel((uint32_t)(line_b - line_lo), zq, line_n, true);
 }
 __host__ __device__ __forceinline__ uint64_t local_alt_sector(uint64_t sec_a, uint64_t key, uint64_t line_lo, uint32_t line_n) {
     const uint64_t line_a = sec_a >> 2;
     if (line_a - line_lo >= line_n) return sec_a;
     return local_alt_line(line_a, (uint32_t)(key & ((1ull << LOCAL_ZQ_BITS) - 1)), line_lo, line_n) * 4 + (sec_a & 3);
-}
-__host__ __device__ __forceinline__ uint64_t local_alt_line_inv(uint64_t line_b, uint32_t zq, uint64_t line_lo, uint32_t line_n) {
-    const uint32_t step = local_alt_step(zq, line_n);
-    uint64_t rel = line_b - line_lo;
-    rel = rel >= step ? rel - step : rel + line_n - step;
-    return line_lo + rel;
 }
 // both candidate sectors (global indices) of c; sec_b == sec_a when the A line is not in this shard
 __host__ __device__ __forceinline__ void local_locate2(uint64_t c, int k, uint64_t NL, uint64_t line_lo, uint32_t line_n,

@@ -971,7 +971,7 @@ int table_build_synthetic(cuclark_db* db, uint32_t seed, uint32_t n_targets, uin
 namespace {
 
 constexpr char CACHE_MAGIC[8] = {'C', 'U', 'C', 'B', '2', 'T', 'B', 'L'};
-constexpr uint32_t CACHE_VERSION = 2;   // 2: LOCAL tables have two candidate lines per minimizer
+constexpr uint32_t CACHE_VERSION = 3;   // 2: LOCAL tables have two candidate lines per minimizer; 3: the second one within 32 KB of the first
 constexpr size_t CACHE_IO_BYTES = 64ull << 20;
 
 struct CacheHeader {                 // 192 bytes, little endian
