@@ -35,7 +35,7 @@ ABI_SYMBOLS = [
     "cuclark_synth_reads_device", "cuclark_synth_fastq_device", "cuclark_gather_bench",
     "cuclark_classify_text", "cuclark_classify_file", "cuclark_text_debug",
     "cuclark_classify_text_multi", "cuclark_classify_file_multi", "cuclark_classify_text_buffer",
-    "cuclark_build_database", "cuclark_save_table", "cuclark_load_table",
+    "cuclark_build_database", "cuclark_save_table", "cuclark_load_table", "cuclark_plan_table",
 ]
 
 
@@ -145,6 +145,22 @@ def load_library():
             fn.restype = ci
     _lib = lib
     return lib
+
+
+class TablePlan(C.Structure):
+    _fields_ = [("layout", C.c_int), ("n_buckets", C.c_uint64), ("n_local_buckets", C.c_uint64), ("home_bytes", C.c_uint64)]
+
+
+def plan_table(k: int, n_entries: int, htsize: int = HTSIZE_FULL, n_targets: int = 1, shard=(0, 1), bucket_load: float = 0.0,
+               layout: int = 0) -> dict:
+    """cuclark_plan_table: the layout and size the loader would choose, no device needed."""
+    lib = load_library()
+    cfg = Config(k, htsize, 0, n_targets, 0, 0, shard[0], shard[1], bucket_load, layout)
+    out = TablePlan()
+    rc = lib.cuclark_plan_table(C.byref(cfg), C.c_uint64(n_entries), C.byref(out))
+    if rc != 0:
+        raise CuclarkError(rc, lib.cuclark_last_error().decode())
+    return {f: getattr(out, f) for f, _ in TablePlan._fields_}
 
 
 def key_bytes_for(k: int, htsize: int) -> int:

@@ -204,6 +204,19 @@ int cuclark_build_db_synthetic(cuclark_db* db, uint32_t seed, uint32_t n_targets
     return table_build_synthetic(db, seed, n_targets, genome_len, light_gap);
 }
 
+int cuclark_plan_table(const cuclark_config* cfg_in, uint64_t n_entries, cuclark_table_plan* out) {
+    if (!cfg_in || !out) { set_error("null argument"); return CUCLARK_ERR_ARG; }
+    if (cfg_in->k < 2 || cfg_in->k > 32) { set_error("The k-mer length should be in [2,32]."); return CUCLARK_ERR_ARG; }
+    cuclark_config cfg = *cfg_in;
+    if (cfg.shard_count < 1) { cfg.shard_count = 1; cfg.shard_index = 0; }
+    if (cfg.layout == 0) {
+        const char* e = getenv("CUCLARK_LAYOUT");
+        if (e && e[0] >= '1' && e[0] <= '3' && !e[1]) cfg.layout = e[0] - '0';
+    }
+    table_plan(cfg, n_entries, out);
+    return CUCLARK_OK;
+}
+
 int cuclark_get_stats(cuclark_db* db, cuclark_stats* s) {
     if (!db || !s) { set_error("null argument"); return CUCLARK_ERR_ARG; }
     memset(s, 0, sizeof *s);

@@ -83,6 +83,7 @@ int table_build_from_arrays(cuclark_db* db, const uint8_t* sz, const void* ky, c
                             uint64_t n_entries_file, int sfactor, const char* base_path);
 int table_build_synthetic(cuclark_db* db, uint32_t seed, uint32_t n_targets, uint64_t genome_len, int light_gap);
 void table_free(cuclark_db* db);
+void table_plan(const cuclark_config& cfg, uint64_t n_entries, cuclark_table_plan* out);
 int table_save(cuclark_db* db, const char* path);
 int table_load(cuclark_db* db, const char* path, const char* src_base, int sfactor);
 

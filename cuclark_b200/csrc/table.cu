@@ -688,6 +688,14 @@ int finish_build(cuclark_db* db, const Geometry& g, BuildBuffers& b, BuildCtx& x
 
 }  // namespace
 
+void table_plan(const cuclark_config& cfg, uint64_t n_entries, cuclark_table_plan* out) {
+    const Geometry g = choose_geometry(cfg, n_entries, 1.0);
+    out->layout = g.layout;
+    out->n_buckets = g.M;
+    out->n_local_buckets = g.n_local;
+    out->home_bytes = g.n_local * 32;
+}
+
 void table_free(cuclark_db* db) {
     if (db->d_table) cudaFree(db->d_table);
     if (db->d_ovf) cudaFree(db->d_ovf);

@@ -123,6 +123,18 @@ int cuclark_build_db_synthetic(cuclark_db* db, uint32_t seed, uint32_t n_targets
 int cuclark_save_table(cuclark_db* db, const char* path);
 int cuclark_load_table(cuclark_db* db, const char* path, const char* src_base, int sfactor);
 
+/* What cuclark_load_db_* would build for a database of n_entries k-mers under cfg, without touching a device:
+ * the layout the automatic choice takes, the bucket count and the bytes of the home table (the overflow table
+ * comes on top: ~3 % of the entries at 27 B each). For sizing a run and for the reference's dbParts logic
+ * (src/CuClarkDB.cu:543-574 decides the number of swap cycles from the same figures; here it is always 1). */
+typedef struct cuclark_table_plan {
+    int layout;                /* 1 narrow, 2 wide, 3 local                                  */
+    uint64_t n_buckets;        /* global 32-byte buckets                                     */
+    uint64_t n_local_buckets;  /* buckets of this shard (cfg.shard_index of cfg.shard_count) */
+    uint64_t home_bytes;       /* n_local_buckets * 32                                       */
+} cuclark_table_plan;
+int cuclark_plan_table(const cuclark_config* cfg, uint64_t n_entries, cuclark_table_plan* out);
+
 int cuclark_get_stats(cuclark_db* db, cuclark_stats* out);
 /* Fetch the counters (lookups, dense_reads, truncated_rows) of the last
  * cuclark_classify_device call; synchronises `stream` (NULL = library stream). */

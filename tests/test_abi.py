@@ -65,3 +65,28 @@ def test_key_width_dispatch():
     assert api.key_bytes_for(32, api.HTSIZE_FULL) == 8
     assert api.key_bytes_for(27, api.HTSIZE_LIGHT) == 4
     assert api.key_bytes_for(20, api.HTSIZE_LIGHT) == 2
+
+
+def test_plan_table_picks_the_layout_without_a_device(monkeypatch):
+    """cuclark_plan_table: which device layout the loader takes for a database of a given size (no GPU needed)."""
+    monkeypatch.delenv("CUCLARK_LAYOUT", raising=False)
+    monkeypatch.delenv("CUCLARK_NO_LOCAL", raising=False)
+    # BASELINE configs[1]: k=31, 5.72 G entries on one device -> minimizer lines at their minimum count (2^29 + 1 lines)
+    p = api.plan_table(31, 5_719_957_086)
+    assert p["layout"] == 3 and p["n_buckets"] == 4 * ((1 << 29) + 1) and p["home_bytes"] == p["n_buckets"] * 32
+    # the 2,000-target reading (8 G entries): still LOCAL, 12 entries per line
+    p = api.plan_table(31, 7_999_939_980)
+    assert p["layout"] == 3 and 80e9 < p["home_bytes"] < 90e9
+    # a shard of a table-partitioned run, and a small database, stay on the hashed sectors
+    p = api.plan_table(31, 5_719_957_086, shard=(3, 8))
+    assert p["layout"] == 1 and abs(p["n_local_buckets"] - p["n_buckets"] / 8) <= 1
+    assert api.plan_table(27, 185_000, htsize=api.HTSIZE_LIGHT)["layout"] == 1
+    assert api.plan_table(31, 1_000_000)["layout"] == 2          # k=31 small: 64-bit keys
+    # forcing LOCAL where its minimum table (4^(k-7)/2^19 lines) would be mostly empty falls back to the hashed layouts;
+    # at k=27 the minimum is 2^21 (+1) lines (268 MB) and is accepted
+    assert api.plan_table(31, 1_000_000, layout=3)["layout"] == 2
+    p = api.plan_table(27, 185_000, htsize=api.HTSIZE_LIGHT, layout=3)
+    assert p["layout"] == 3 and p["n_buckets"] == 4 * ((1 << 21) + 1)
+    # the automatic choice can be switched off
+    monkeypatch.setenv("CUCLARK_NO_LOCAL", "1")
+    assert api.plan_table(31, 5_719_957_086)["layout"] == 1
