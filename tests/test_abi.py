@@ -90,3 +90,20 @@ def test_plan_table_picks_the_layout_without_a_device(monkeypatch):
     # the automatic choice can be switched off
     monkeypatch.setenv("CUCLARK_NO_LOCAL", "1")
     assert api.plan_table(31, 5_719_957_086)["layout"] == 1
+
+
+def test_ctypes_structs_match_the_header(tmp_path):
+    """Every struct that crosses the C ABI has the same size in include/cuclark_b200.h (compiled with gcc as plain C)
+    and in the ctypes mirror the tests and the bench use."""
+    import subprocess
+    pairs = [("cuclark_config", api.Config), ("cuclark_stats", api.Stats), ("cuclark_table_plan", api.TablePlan),
+             ("cuclark_build_opts", api.BuildOpts), ("cuclark_build_stats", api.BuildStats),
+             ("cuclark_text_opts", api.TextOpts), ("cuclark_text_stats", api.TextStats), ("cuclark_text_arrays", api.TextArrays)]
+    src = tmp_path / "sizes.c"
+    src.write_text('#include <stdio.h>\n#include "cuclark_b200.h"\nint main(void) {\n' +
+                   "".join(f'  printf("{c} %zu\\n", sizeof({c}));\n' for c, _ in pairs) + "  return 0;\n}\n")
+    exe = tmp_path / "sizes"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    sizes = dict(line.split() for line in subprocess.check_output([str(exe)], text=True).splitlines())
+    for cname, ct in pairs:
+        assert int(sizes[cname]) == ctypes.sizeof(ct), (cname, sizes[cname], ctypes.sizeof(ct))
