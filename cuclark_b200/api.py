@@ -26,7 +26,7 @@ FINAL_ROW = 5                # m_finalResultsRowSize, src/CuCLARK_hh.hh:1593
 
 # every symbol include/cuclark_b200.h declares
 ABI_SYMBOLS = [
-    "cuclark_last_error", "cuclark_version", "cuclark_create", "cuclark_destroy",
+    "cuclark_last_error", "cuclark_version", "cuclark_kernel_launches", "cuclark_create", "cuclark_destroy",
     "cuclark_load_db_files", "cuclark_load_db_arrays", "cuclark_build_db_synthetic",
     "cuclark_get_stats", "cuclark_sync_stats",
     "cuclark_batches_alloc", "cuclark_batch_buffers", "cuclark_batch_ready", "cuclark_batch_query",
@@ -36,6 +36,9 @@ ABI_SYMBOLS = [
     "cuclark_classify_text", "cuclark_classify_file", "cuclark_text_debug",
     "cuclark_classify_text_multi", "cuclark_classify_file_multi", "cuclark_classify_text_buffer",
     "cuclark_build_database", "cuclark_save_table", "cuclark_load_table", "cuclark_plan_table",
+    "cuclark_route_alloc", "cuclark_route_free", "cuclark_route_export", "cuclark_route_import", "cuclark_route_connect",
+    "cuclark_route_scatter", "cuclark_route_probe", "cuclark_route_gather", "cuclark_route_get_stats",
+    "cuclark_classify_routed_device", "cuclark_clone_table", "cuclark_device_info",
 ]
 
 
@@ -92,6 +95,12 @@ class BuildStats(C.Structure):
                 ("key_bytes", C.c_int)]
 
 
+class RouteStats(C.Structure):
+    _fields_ = [("n_ranks", C.c_int), ("rank", C.c_int), ("region_bytes", C.c_uint64), ("map_bytes", C.c_uint64),
+                ("cap_blocks", C.c_uint64), ("lookups", C.c_uint64), ("probed", C.c_uint64), ("blocks", C.c_uint64),
+                ("blocks_remote", C.c_uint64), ("err", C.c_uint32)]
+
+
 SINK_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64)
 
 _lib = None
@@ -102,11 +111,13 @@ def load_library():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    # CUCLARK_LIB: another build of the same library (kernel variants under lib/variants/, tools/kernel_variants.py)
+    path = os.environ.get("CUCLARK_LIB") or LIB_PATH
+    if not os.path.exists(path):
         raise FileNotFoundError(
-            f"{LIB_PATH} is missing: build it with `python -m cuclark_b200.build` "
+            f"{path} is missing: build it with `python -m cuclark_b200.build` "
             "(there is no CPU fallback)")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     u64, u32, u16, u8, sz, vp, ci = C.c_uint64, C.c_uint32, C.c_uint16, C.c_uint8, C.c_size_t, C.c_void_p, C.c_int
     P = C.POINTER
     lib.cuclark_last_error.restype = C.c_char_p
@@ -139,16 +150,34 @@ def load_library():
     lib.cuclark_save_table.argtypes = [vp, C.c_char_p]
     lib.cuclark_load_table.argtypes = [vp, C.c_char_p, C.c_char_p, ci]
     lib.cuclark_classify_file_multi.argtypes = [P(vp), ci, C.c_char_p, C.c_char_p, P(TextOpts), P(TextStats)]
+    lib.cuclark_clone_table.argtypes = [vp, vp]
+    lib.cuclark_device_info.argtypes = [ci, P(ci), P(u64), P(u64)]
+    lib.cuclark_route_alloc.argtypes = [vp, ci, sz]
+    lib.cuclark_route_free.argtypes = [vp]
+    lib.cuclark_route_export.argtypes = [vp, vp, P(u64)]
+    lib.cuclark_route_import.argtypes = [vp, ci, vp]
+    lib.cuclark_route_connect.argtypes = [P(vp), ci]
+    lib.cuclark_route_scatter.argtypes = [vp, vp, vp, sz, sz, vp]
+    lib.cuclark_route_probe.argtypes = [vp, vp]
+    lib.cuclark_route_gather.argtypes = [vp, vp, vp, sz, sz, vp, vp, vp]
+    lib.cuclark_route_get_stats.argtypes = [vp, P(RouteStats)]
+    lib.cuclark_classify_routed_device.argtypes = [P(vp), ci, P(vp), P(vp), P(sz), P(sz), P(vp), P(vp)]
     for name in ABI_SYMBOLS:
         fn = getattr(lib, name)
-        if name != "cuclark_last_error":
+        if name not in ("cuclark_last_error", "cuclark_kernel_launches"):
             fn.restype = ci
+    lib.cuclark_kernel_launches.restype = u64
     _lib = lib
     return lib
 
 
 class TablePlan(C.Structure):
     _fields_ = [("layout", C.c_int), ("n_buckets", C.c_uint64), ("n_local_buckets", C.c_uint64), ("home_bytes", C.c_uint64)]
+
+
+def kernel_launches() -> int:
+    """Hot-path kernels launched by the library in this process so far (cuclark_kernel_launches)."""
+    return int(load_library().cuclark_kernel_launches())
 
 
 def plan_table(k: int, n_entries: int, htsize: int = HTSIZE_FULL, n_targets: int = 1, shard=(0, 1), bucket_load: float = 0.0,
@@ -274,6 +303,10 @@ class CuClarkDB:
         self._check(rc)
         return True
 
+    def clone_table_from(self, src: "CuClarkDB"):
+        """Take a device-to-device copy of `src`'s loaded table (cuclark_clone_table)."""
+        self._check(self._lib.cuclark_clone_table(src._h, self._h))
+
     def build_synthetic(self, seed: int, n_targets: int, genome_len: int, light_gap: int = 0):
         self._check(self._lib.cuclark_build_db_synthetic(self._h, seed, n_targets, genome_len, light_gap))
 
@@ -343,6 +376,39 @@ class CuClarkDB:
                           stream: int = 0):
         self._check(self._lib.cuclark_merge_rows_device(self._h, d_parts, n_parts, n_reads, d_rows_out or None,
                                                          d_final or None, stream or None))
+
+    # -- table-partitioned mode by k-mer routing (include/cuclark_b200.h, csrc/route.cu) ------------------------
+    def route_alloc(self, n_ranks: int, max_containers: int):
+        self._check(self._lib.cuclark_route_alloc(self._h, n_ranks, max_containers))
+
+    def route_free(self):
+        self._check(self._lib.cuclark_route_free(self._h))
+
+    def route_export(self) -> bytes:
+        """64-byte CUDA IPC handle of this rank's region (one process per GPU: send it to the other ranks)."""
+        buf = C.create_string_buffer(64)
+        self._check(self._lib.cuclark_route_export(self._h, buf, None))
+        return buf.raw
+
+    def route_import(self, peer_rank: int, handle: bytes):
+        buf = C.create_string_buffer(handle, 64)
+        self._check(self._lib.cuclark_route_import(self._h, peer_rank, buf))
+
+    def route_scatter(self, d_ptr: int, d_cont: int, n_reads: int, n_cont: int, stream: int = 0):
+        self._check(self._lib.cuclark_route_scatter(self._h, d_ptr, d_cont, n_reads, n_cont, stream or None))
+
+    def route_probe(self, stream: int = 0):
+        self._check(self._lib.cuclark_route_probe(self._h, stream or None))
+
+    def route_gather(self, d_ptr: int, d_cont: int, n_reads: int, n_cont: int, d_final: int = 0, d_rows: int = 0,
+                     stream: int = 0):
+        self._check(self._lib.cuclark_route_gather(self._h, d_ptr, d_cont, n_reads, n_cont, d_final or None,
+                                                    d_rows or None, stream or None))
+
+    def route_stats(self) -> dict:
+        s = RouteStats()
+        self._check(self._lib.cuclark_route_get_stats(self._h, C.byref(s)))
+        return {f: getattr(s, f) for f, _ in RouteStats._fields_}
 
     def synth_reads_device(self, seed, genome_seed, n_targets, genome_len, first_read, n_reads, read_len,
                            pct_random, sub_per_10k, d_ptr: int, d_cont: int, stream: int = 0):
@@ -433,3 +499,35 @@ class CuClarkDB:
         n, nc = st.n_reads, st.n_containers
         out = {k: (v[:n + 1] if k == "reads_ptr" else v[:nc] if k == "containers" else v[:n]) for k, v in arrs.items()}
         return out, st.as_dict()
+
+
+def device_info(device: int = 0) -> dict:
+    lib = load_library()
+    n, f, t = C.c_int(), C.c_uint64(), C.c_uint64()
+    rc = lib.cuclark_device_info(device, C.byref(n), C.byref(f), C.byref(t))
+    if rc != 0:
+        raise CuclarkError(rc, lib.cuclark_last_error().decode())
+    return {"n_devices": n.value, "free_bytes": f.value, "total_bytes": t.value}
+
+
+def route_connect(handles):
+    """N handles of THIS process, in rank order (cuclark_route_connect): peer access + plain pointers."""
+    lib = load_library()
+    arr = (C.c_void_p * len(handles))(*[h._h for h in handles])
+    rc = lib.cuclark_route_connect(arr, len(handles))
+    if rc != 0:
+        raise CuclarkError(rc, lib.cuclark_last_error().decode())
+
+
+def classify_routed_device(handles, d_ptrs, d_conts, n_reads, n_conts, d_finals=None, d_rows=None):
+    """cuclark_classify_routed_device: scatter | barrier | probe | barrier | gather for the connected handles of
+    this process; per rank its device pointers (ints) and counts. Synchronises every rank's library stream."""
+    lib = load_library()
+    n = len(handles)
+    vp = C.c_void_p * n
+    szs = C.c_size_t * n
+    rc = lib.cuclark_classify_routed_device(
+        vp(*[h._h for h in handles]), n, vp(*d_ptrs), vp(*d_conts), szs(*n_reads), szs(*n_conts),
+        vp(*[x or None for x in d_finals]) if d_finals else None, vp(*[x or None for x in d_rows]) if d_rows else None)
+    if rc != 0:
+        raise CuclarkError(rc, lib.cuclark_last_error().decode())

@@ -18,8 +18,8 @@ LIB = os.path.join(LIBDIR, "libcuclark_b200.so")
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-CU_SOURCES = ["table.cu", "classify.cu", "capi.cu", "textpipe.cu", "stream.cu", "dbbuild.cu"]
-HEADERS = ["common.cuh", "internal.h", "synth.cuh", "textpipe.cuh", "fmt_g.h", os.path.join("..", "..", "include", "cuclark_b200.h")]
+CU_SOURCES = ["table.cu", "classify.cu", "route.cu", "capi.cu", "textpipe.cu", "stream.cu", "dbbuild.cu"]
+HEADERS = ["common.cuh", "internal.h", "hits.cuh", "kmerwin.cuh", "synth.cuh", "textpipe.cuh", "fmt_g.h", os.path.join("..", "..", "include", "cuclark_b200.h")]
 
 
 def _newer(target: str, deps: list[str]) -> bool:
@@ -40,6 +40,21 @@ def build_lib(verbose: bool = False, force: bool = False) -> str:
             cmd += ["-Xptxas", "-v"]
         subprocess.check_call(cmd)
     return LIB
+
+
+def build_variant(name: str, defines: list[str], verbose: bool = False) -> str:
+    """The same library with other compile-time choices (-DCUCLARK_...=...), for A/B timing on the GPU box:
+    cuclark_b200/lib/variants/<name>.so, picked up through CUCLARK_LIB."""
+    out_dir = os.path.join(LIBDIR, "variants")
+    os.makedirs(out_dir, exist_ok=True)
+    out = os.path.join(out_dir, name + ".so")
+    srcs = [os.path.join(CSRC, s) for s in CU_SOURCES]
+    cmd = [NVCC, *ARCH, "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC,-O3", "-shared",
+           "-ccbin", "/usr/bin/g++", "-o", out, *[f"-D{d}" for d in defines], *srcs]
+    if verbose:
+        cmd += ["-Xptxas", "-v"]
+    subprocess.check_call(cmd)
+    return out
 
 
 def build_all(verbose: bool = False, force: bool = False) -> None:

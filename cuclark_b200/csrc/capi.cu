@@ -19,6 +19,7 @@
 namespace cuclark {
 
 static thread_local char g_err[512] = "";
+std::atomic<uint64_t> g_kernel_launches{0};
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -91,7 +92,8 @@ using namespace cuclark;
 extern "C" {
 
 const char* cuclark_last_error(void) { return g_err; }
-int cuclark_version(void) { return 100; }
+int cuclark_version(void) { return 200; }
+uint64_t cuclark_kernel_launches(void) { return g_kernel_launches.load(std::memory_order_relaxed); }
 
 int cuclark_create(const cuclark_config* cfg, cuclark_db** out) {
     if (!cfg || !out) { set_error("null argument"); return CUCLARK_ERR_ARG; }
@@ -152,6 +154,7 @@ int cuclark_destroy(cuclark_db* db) {
     cudaDeviceSynchronize();
     free_batches(db);
     text_pipe_free(db);
+    route_free(db);
     table_free(db);
     free_scratch(db->scratch);
     cudaFree(db->d_dense_hist);
@@ -193,6 +196,30 @@ int cuclark_load_table(cuclark_db* db, const char* path, const char* src_base, i
     if (rc) return rc;
     table_free(db);
     return table_load(db, path, src_base, sfactor);
+}
+
+int cuclark_clone_table(cuclark_db* src, cuclark_db* dst) {
+    if (!src || !dst || src == dst) { set_error("bad argument"); return CUCLARK_ERR_ARG; }
+    return table_clone(src, dst);
+}
+
+int cuclark_device_info(int device, int* n_devices, uint64_t* free_bytes, uint64_t* total_bytes) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device available (there is no CPU fallback)");
+        return CUCLARK_ERR_NO_DEVICE;
+    }
+    if (n_devices) *n_devices = n;
+    if (free_bytes || total_bytes) {
+        if (device < 0 || device >= n) { set_error("device %d not present (%d devices)", device, n); return CUCLARK_ERR_NO_DEVICE; }
+        size_t f = 0, t = 0;
+        CK(cudaSetDevice(device));
+        CK(cudaMemGetInfo(&f, &t));
+        if (free_bytes) *free_bytes = f;
+        if (total_bytes) *total_bytes = t;
+    }
+    return CUCLARK_OK;
 }
 
 int cuclark_build_db_synthetic(cuclark_db* db, uint32_t seed, uint32_t n_targets, uint64_t genome_len, int light_gap) {
@@ -401,6 +428,102 @@ int cuclark_gather_bench(cuclark_db* db, uint64_t n_probes, int bytes_per_probe,
     int rc = use_device(db);
     if (rc) return rc;
     return gather_bench_launch(db, n_probes, bytes_per_probe, ilp, iters, ms_out);
+}
+
+/* ---- table-partitioned mode by k-mer routing (route.cu) ---------------------------------------------- */
+int cuclark_route_alloc(cuclark_db* db, int n_ranks, size_t max_containers) {
+    if (!db) { set_error("null argument"); return CUCLARK_ERR_ARG; }
+    int rc = use_device(db);
+    return rc ? rc : route_alloc(db, n_ranks, max_containers);
+}
+int cuclark_route_free(cuclark_db* db) {
+    if (db) route_free(db);
+    return CUCLARK_OK;
+}
+int cuclark_route_export(cuclark_db* db, void* handle64, uint64_t* region_bytes) {
+    if (!db || !handle64) { set_error("null argument"); return CUCLARK_ERR_ARG; }
+    int rc = use_device(db);
+    return rc ? rc : route_export(db, handle64, region_bytes);
+}
+int cuclark_route_import(cuclark_db* db, int peer_rank, const void* handle64) {
+    if (!db || !handle64) { set_error("null argument"); return CUCLARK_ERR_ARG; }
+    int rc = use_device(db);
+    return rc ? rc : route_import(db, peer_rank, handle64);
+}
+int cuclark_route_connect(cuclark_db* const* dbs, int n) {
+    if (!dbs || n < 1 || n > CUCLARK_ROUTE_MAX_RANKS) { set_error("bad argument"); return CUCLARK_ERR_ARG; }
+    return route_connect(dbs, n);
+}
+int cuclark_route_scatter(cuclark_db* db, const uint32_t* d_reads_ptr, const uint16_t* d_containers, size_t n_reads,
+                          size_t n_containers, void* stream) {
+    if (!db || (!d_reads_ptr && n_reads)) { set_error("null argument"); return CUCLARK_ERR_ARG; }
+    int rc = use_device(db);
+    return rc ? rc : route_scatter(db, d_reads_ptr, d_containers, n_reads, n_containers, stream ? (cudaStream_t)stream : db->stream);
+}
+int cuclark_route_probe(cuclark_db* db, void* stream) {
+    if (!db) { set_error("null argument"); return CUCLARK_ERR_ARG; }
+    int rc = use_device(db);
+    return rc ? rc : route_probe(db, stream ? (cudaStream_t)stream : db->stream);
+}
+int cuclark_route_gather(cuclark_db* db, const uint32_t* d_reads_ptr, const uint16_t* d_containers, size_t n_reads,
+                         size_t n_containers, uint16_t* d_final5, uint16_t* d_rows, void* stream) {
+    if (!db || (!d_reads_ptr && n_reads)) { set_error("null argument"); return CUCLARK_ERR_ARG; }
+    int rc = use_device(db);
+    return rc ? rc : route_gather(db, db->scratch, d_reads_ptr, d_containers, n_reads, n_containers, d_final5, d_rows,
+                                  stream ? (cudaStream_t)stream : db->stream);
+}
+int cuclark_route_get_stats(cuclark_db* db, cuclark_route_stats* out) {
+    if (!db || !out) { set_error("null argument"); return CUCLARK_ERR_ARG; }
+    return route_stats(db, out);
+}
+
+// scatter on every rank | all ranks wait for all scatters | probe | all wait for all probes | gather
+int cuclark_classify_routed_device(cuclark_db* const* dbs, int n, const uint32_t* const* d_reads_ptr,
+                                   const uint16_t* const* d_containers, const size_t* n_reads, const size_t* n_containers,
+                                   uint16_t* const* d_final5, uint16_t* const* d_rows) {
+    if (!dbs || n < 1 || n > CUCLARK_ROUTE_MAX_RANKS || !d_reads_ptr || !d_containers || !n_reads || !n_containers) {
+        set_error("bad argument");
+        return CUCLARK_ERR_ARG;
+    }
+    cudaEvent_t ev[2][CUCLARK_ROUTE_MAX_RANKS] = {};
+    int rc = CUCLARK_OK;
+    auto done = [&](int r) {
+        for (int ph = 0; ph < 2; ph++)
+            for (int i = 0; i < n; i++)
+                if (ev[ph][i]) { cudaSetDevice(dbs[i]->cfg.device); cudaEventDestroy(ev[ph][i]); }
+        return r;
+    };
+    for (int i = 0; i < n && !rc; i++) {
+        if (!dbs[i]) { set_error("null handle"); return done(CUCLARK_ERR_ARG); }
+        if ((rc = use_device(dbs[i]))) break;
+        for (int ph = 0; ph < 2; ph++)
+            if (cudaEventCreateWithFlags(&ev[ph][i], cudaEventDisableTiming) != cudaSuccess) { set_error("cudaEventCreate failed"); return done(CUCLARK_ERR_CUDA); }
+    }
+    for (int i = 0; i < n && !rc; i++) {
+        if ((rc = use_device(dbs[i]))) break;
+        rc = route_scatter(dbs[i], d_reads_ptr[i], d_containers[i], n_reads[i], n_containers[i], dbs[i]->stream);
+        if (!rc && cudaEventRecord(ev[0][i], dbs[i]->stream) != cudaSuccess) { set_error("cudaEventRecord failed"); rc = CUCLARK_ERR_CUDA; }
+    }
+    for (int i = 0; i < n && !rc; i++) {
+        if ((rc = use_device(dbs[i]))) break;
+        for (int j = 0; j < n; j++)
+            if (j != i && cudaStreamWaitEvent(dbs[i]->stream, ev[0][j], 0) != cudaSuccess) { set_error("cudaStreamWaitEvent failed"); rc = CUCLARK_ERR_CUDA; }
+        if (!rc) rc = route_probe(dbs[i], dbs[i]->stream);
+        if (!rc && cudaEventRecord(ev[1][i], dbs[i]->stream) != cudaSuccess) { set_error("cudaEventRecord failed"); rc = CUCLARK_ERR_CUDA; }
+    }
+    for (int i = 0; i < n && !rc; i++) {
+        if ((rc = use_device(dbs[i]))) break;
+        for (int j = 0; j < n; j++)
+            if (j != i && cudaStreamWaitEvent(dbs[i]->stream, ev[1][j], 0) != cudaSuccess) { set_error("cudaStreamWaitEvent failed"); rc = CUCLARK_ERR_CUDA; }
+        if (!rc) rc = route_gather(dbs[i], dbs[i]->scratch, d_reads_ptr[i], d_containers[i], n_reads[i], n_containers[i],
+                                   d_final5 ? d_final5[i] : nullptr, d_rows ? d_rows[i] : nullptr, dbs[i]->stream);
+    }
+    // the events may be destroyed once the work that waits on them is enqueued; the counters come back with the sync
+    for (int i = 0; i < n && !rc; i++) {
+        if ((rc = use_device(dbs[i]))) break;
+        rc = fetch_counters(dbs[i], dbs[i]->stream);
+    }
+    return done(rc);
 }
 
 /* counters of the last classify on `stream` (synchronises that stream) */

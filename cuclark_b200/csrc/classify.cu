@@ -24,7 +24,9 @@
 // fallback kernel (the reference is undefined beyond MAXHITS).
 #include <algorithm>
 
+#include "hits.cuh"
 #include "internal.h"
+#include "kmerwin.cuh"
 #include "synth.cuh"
 
 namespace cuclark {
@@ -35,7 +37,6 @@ namespace {
 #define CUCLARK_WPB 8
 #endif
 constexpr int WARPS_PER_BLOCK = CUCLARK_WPB;
-constexpr int TSLOTS = 64;            // per-warp hash slots
 constexpr int ILP_ROUNDS = 4;         // independent probes per lane
 #ifndef CUCLARK_ILP_LOCAL
 #define CUCLARK_ILP_LOCAL 1
@@ -45,9 +46,7 @@ constexpr int ILP_ROUNDS = 4;         // independent probes per lane
 #endif
 constexpr int ILP_LOCAL = CUCLARK_ILP_LOCAL;                // LOCAL layout: rows per group (more resident warps instead)
 constexpr int LOCAL_MIN_BLOCKS = CUCLARK_LOCAL_MIN_BLOCKS;  // resident blocks per SM asked of ptxas for the LOCAL kernel
-constexpr int CHUNK_ROUNDS = 31;      // rounds of 32 k-mers served by one set of 32 words
-constexpr int MAX_ROW_PAIRS = 63;
-constexpr uint32_t EMPTY = 0xFFFFFFFFu;
+constexpr int READS_PER_CHUNK = 31;   // one coalesced load of 32 container offsets delimits 31 reads
 constexpr int COUNTER_CHUNK = 4;      // dynamic work counter (reset with the other counters)
 
 struct ClassifyParams {
@@ -55,149 +54,83 @@ struct ClassifyParams {
     const uint32_t* reads_ptr;
     const uint16_t* cont;
     uint32_t n_reads;
-    uint16_t* final5;
-    uint16_t* rows;
-    int row_pairs;
     uint32_t n_targets;
-    uint32_t* counters;
-    uint32_t* dense_list;
-    uint32_t dense_cap;
+    HitSink out;
 };
-
-__device__ __forceinline__ uint64_t shfl64(uint64_t v, int src) {
-    uint32_t lo = __shfl_sync(0xFFFFFFFFu, (uint32_t)v, src);
-    uint32_t hi = __shfl_sync(0xFFFFFFFFu, (uint32_t)(v >> 32), src);
-    return ((uint64_t)hi << 32) | lo;
-}
-
-// top 64 bits of the 128-bit value (hi:lo) << s, 0 <= s <= 62: the 32 nucleotides that start s/2 nucleotides into
-// word hi. Two 32-bit funnel shifts (which take the amount mod 32) over operands picked by s >= 32.
-__device__ __forceinline__ uint64_t window64(uint64_t hi, uint64_t lo, int s) {
-    const uint32_t h1 = (uint32_t)(hi >> 32), h0 = (uint32_t)hi, l1 = (uint32_t)(lo >> 32), l0 = (uint32_t)lo;
-    const bool big = s >= 32;
-    const uint32_t a = big ? h0 : h1, b = big ? l1 : h0, c = big ? l0 : l1;
-    return ((uint64_t)__funnelshift_l(b, a, s) << 32) | __funnelshift_l(c, b, s);
-}
-
-// leader-only insert of (label, n) into the warp's table; false if it is full
-__device__ __forceinline__ bool tab_add(uint32_t* tkey, uint32_t* tcnt, uint32_t label, uint32_t n) {
-    uint32_t slot = (label * 0x9E3779B1u) >> 26;          // 6 bits
-#pragma unroll 1
-    for (int i = 0; i < TSLOTS; i++) {
-        const uint32_t old = atomicCAS(&tkey[slot], EMPTY, label);
-        if (old == EMPTY || old == label) { atomicAdd(&tcnt[slot], n); return true; }
-        slot = (slot + 1) & (TSLOTS - 1);
-    }
-    return false;
-}
-
-// 64-bit words (32 nt each, MSB first) of up to 128 consecutive containers held as four
-// 32-lane windows: lane j gets containers 4j..4j+3. Only the first nwin windows are live.
-__device__ __forceinline__ uint64_t assemble_words(const uint32_t (&wv)[4], int nwin, int lane) {
-    uint64_t W = 0;
-    const int src = 4 * (lane & 7);
-#pragma unroll
-    for (int u = 0; u < 4; u++) {
-        if (u < nwin) {                                   // warp-uniform
-            uint64_t w = 0;
-#pragma unroll
-            for (int t = 0; t < 4; t++)
-                w |= (uint64_t)__shfl_sync(0xFFFFFFFFu, wv[u], src + t) << (48 - 16 * t);
-            if ((lane >> 3) == u) W = w;
-        }
-    }
-    return W;
-}
 
 template <int LAYOUT, bool ROWS>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, LAYOUT == LAYOUT_LOCAL ? LOCAL_MIN_BLOCKS : 2) k_classify(const ClassifyParams p) {
     __shared__ uint32_t s_key[WARPS_PER_BLOCK][TSLOTS];
     __shared__ uint32_t s_cnt[WARPS_PER_BLOCK][TSLOTS];
     __shared__ uint16_t s_row[ROWS ? WARPS_PER_BLOCK : 1][ROWS ? 2 * MAX_ROW_PAIRS + 2 : 2];
+    __shared__ uint32_t s_ptr[WARPS_PER_BLOCK][36];     // 32 container offsets, first read, number of reads, current read
 
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     uint32_t* tkey = s_key[wib];
     uint32_t* tcnt = s_cnt[wib];
-    tkey[lane] = EMPTY; tkey[lane + 32] = EMPTY;
-    tcnt[lane] = 0; tcnt[lane + 32] = 0;
-    __syncwarp();
+    uint32_t* sptr = s_ptr[wib];
+    tab_clear(tkey, tcnt, lane);
 
     constexpr int ILP = LAYOUT == LAYOUT_LOCAL ? ILP_LOCAL : ILP_ROUNDS;
     const TableView& T = p.t;
     const int k = T.k;
     const int kshift = 64 - 2 * k;
-    const int pitch = 2 * p.row_pairs + 2;
-    unsigned long long my_lookups = 0;
+    uint32_t my_lookups = 0;          // per lane, flushed after every chunk of 31 reads (and before it can wrap)
 
-    // Each warp pulls chunks of 32 consecutive reads from a global counter (dynamic
-    // balance); one coalesced load fetches the chunk's 33 container offsets.
+    auto flush_lookups = [&] {             // one atomic per warp and chunk of 31 reads
+        const unsigned long long tot = (unsigned long long)__reduce_add_sync(0xFFFFFFFFu, my_lookups & 0xFFFFu) +
+                                       ((unsigned long long)__reduce_add_sync(0xFFFFFFFFu, my_lookups >> 16) << 16);
+        if (lane == 0 && tot) atomicAdd(reinterpret_cast<unsigned long long*>(p.out.counters + COUNTER_LOOKUPS), tot);
+        my_lookups = 0;
+    };
+    // Each warp pulls chunks of 31 consecutive reads from a global counter (dynamic
+    // balance); one coalesced load fetches the chunk's 32 container offsets.
     for (;;) {
         uint32_t chunk = 0;
-        if (lane == 0) chunk = atomicAdd(&p.counters[COUNTER_CHUNK], 1u);
+        if (lane == 0) chunk = atomicAdd(&p.out.counters[COUNTER_CHUNK], 1u);
         chunk = __shfl_sync(0xFFFFFFFFu, chunk, 0);
-        const uint64_t base64 = (uint64_t)chunk * 32;
+        const uint64_t base64 = (uint64_t)chunk * READS_PER_CHUNK;
         if (base64 >= p.n_reads) break;
-        const uint32_t base = (uint32_t)base64;
-        const uint32_t nr = min(32u, p.n_reads - base);
-        const uint32_t my_ptr = p.reads_ptr[min(base + lane, p.n_reads)];
-        const uint32_t last_ptr = p.reads_ptr[min(base + 32u, p.n_reads)];
-
-        // prefetched first header + first 32-container window of the next read
-        uint32_t pf_hdr = 0, pf_win = 0;
         {
-            const uint32_t p0 = __shfl_sync(0xFFFFFFFFu, my_ptr, 0), e0 = nr > 1 ? __shfl_sync(0xFFFFFFFFu, my_ptr, 1) : last_ptr;
-            if (p0 < e0) pf_hdr = p.cont[p0];
-            if (p0 + 1 + lane < e0) pf_win = p.cont[p0 + 1 + lane];
+            const uint32_t base = (uint32_t)base64;
+            // the chunk's state is parked in shared memory: it is touched once per read, the registers are the row loop's
+            __syncwarp();
+            sptr[lane] = p.reads_ptr[min(base + lane, p.n_reads)];   // entry i: start of read i = end of read i-1
+            if (lane == 0) { sptr[32] = base; sptr[33] = min((uint32_t)READS_PER_CHUNK, p.n_reads - base); sptr[34] = 0; }
+            __syncwarp();
         }
 
-        for (uint32_t ri = 0; ri < nr; ri++) {
-            const uint32_t read = base + ri;
-            uint32_t pos = __shfl_sync(0xFFFFFFFFu, my_ptr, ri);
-            const uint32_t end = ri + 1 < 32 ? __shfl_sync(0xFFFFFFFFu, my_ptr, (ri + 1) & 31) : last_ptr;
-            const uint32_t cur_hdr = pf_hdr, cur_win = pf_win;
-            if (ri + 1 < nr) {                              // prefetch the next read while this one probes
-                const uint32_t pn = end;
-                const uint32_t en = ri + 2 < 32 ? __shfl_sync(0xFFFFFFFFu, my_ptr, (ri + 2) & 31) : last_ptr;
-                pf_hdr = pn < en ? p.cont[pn] : 0;
-                pf_win = pn + 1 + lane < en ? p.cont[pn + 1 + lane] : 0;
-            }
-            uint32_t first_label = NO_LABEL, first_cnt = 0, total = 0, my_same = 0;
-            bool table_mode = false, overflow = false;
-            bool first_part = true;
-            // hits of one row of 32 k-mers into the read's counters (warp-collective)
-            // hits of one row of 32 k-mers into the read's counters (warp-collective). While every hit of the
-            // read went to ONE target (the usual case) each lane just counts its own hits: one vote per row.
-            auto account = [&](const uint32_t label) {
-                uint32_t hitmask = 0;
-                if (!table_mode) {
-                    if (first_label == NO_LABEL) {
-                        hitmask = __ballot_sync(0xFFFFFFFFu, label != NO_LABEL);
-                        if (!hitmask) return;
-                        first_label = __shfl_sync(0xFFFFFFFFu, label, __ffs(hitmask) - 1);
-                    }
-                    const bool hit = label != NO_LABEL;
-                    if (!__any_sync(0xFFFFFFFFu, hit && label != first_label)) { my_same += hit; return; }
-                    // a second target: fold the per-lane counts and continue in the shared-memory table
-                    first_cnt = __reduce_add_sync(0xFFFFFFFFu, my_same);
-                    total = first_cnt;
-                    table_mode = true;
-                    if (lane == 0 && first_cnt) tab_add(tkey, tcnt, first_label, first_cnt);
-                    __syncwarp();
-                }
-                hitmask = __ballot_sync(0xFFFFFFFFu, label != NO_LABEL);
-                if (!hitmask) return;
-                total += __popc(hitmask);
-                const uint32_t grp = __match_any_sync(0xFFFFFFFFu, label);
-                bool ok = true;
-                if (label != NO_LABEL && lane == __ffs(grp) - 1) ok = tab_add(tkey, tcnt, label, __popc(grp));
-                if (__any_sync(0xFFFFFFFFu, !ok)) overflow = true;
-                __syncwarp();
-            };
+        // prefetched first 32 containers of the next read: lane 0 its first part header, lane j container j-1
+        uint32_t pf = 0;
+        {
+            const uint32_t p0 = sptr[0], e0 = sptr[1];
+            if (p0 + lane < e0) pf = p.cont[p0 + lane];
+        }
 
+        for (;;) {
+            __syncwarp();
+            const uint32_t ri = sptr[34];                   // (the loop counter lives in shared memory too)
+            if (ri >= sptr[33]) break;
+            if (__any_sync(0xFFFFFFFFu, my_lookups >= (1u << 30))) flush_lookups();     // a read adds < 2^30 per lane
+            uint32_t pos = sptr[ri];
+            const uint32_t end = sptr[ri + 1];
+            const uint32_t cur = pf;
+            if (ri + 1 < sptr[33]) {                        // prefetch the next read while this one probes
+                const uint32_t pn = end;
+                const uint32_t en = sptr[ri + 2];
+                pf = pn + lane < en ? p.cont[pn + lane] : 0;
+            }
+            __syncwarp();
+            if (lane == 0) sptr[34] = ri + 1;
+            const uint32_t cur_hdr = __shfl_sync(0xFFFFFFFFu, cur, 0);
+            uint32_t cur_win = __shfl_down_sync(0xFFFFFFFFu, cur, 1);                    // lane 31: loaded on demand
+            WarpHits hits;
+            bool first_part = true;
             while (pos < end) {
-                const uint32_t L = first_part ? cur_hdr : (uint32_t)p.cont[pos];
+                const uint32_t Lraw = first_part ? cur_hdr : (uint32_t)p.cont[pos];
                 const uint32_t first = pos + 1;
-                const uint32_t ncont = (L + 7) >> 3;
+                uint32_t L;
+                const uint32_t ncont = part_extent(Lraw, first, end, L);
                 pos = first + ncont;                         // start of the next part
                 const int nk = (int)L - k + 1;
                 for (int cb = 0; cb < nk; cb += 32 * CHUNK_ROUNDS) {
@@ -208,13 +141,13 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, LAYOUT == LAYOUT_LOCAL ?
 #pragma unroll
                     for (int u = 0; u < 4; u++) {
                         const uint32_t ci = first + co + 32 * u + lane;
-                        if (u == 0 && first_part && cb == 0) wv[u] = cur_win;
+                        if (u == 0 && first_part && cb == 0) wv[u] = lane < 31 ? cur_win : ncont > 31 ? (uint32_t)p.cont[first + 31] : 0u;
                         else wv[u] = (u < nwin && ci < pos) ? (uint32_t)p.cont[ci] : 0u;
                     }
                     const uint64_t W = assemble_words(wv, nwin, lane);
                     const int rounds = min(CHUNK_ROUNDS, (nk - cb + 31) >> 5);
                     bool have_carry = false;                 // LOCAL: hash row handed over from the previous group
-                    uint64_t carry_z = 0, carry_x = 0, carry_rc = 0;
+                    uint64_t carry_z = 0, carry_c = 0;       // carry_z bit 61: the k-mer stands in its canonical form
                     uint32_t carry_oh = 0;
                     const int m_limit = (int)L - (k - LOCAL_W + 1) - cb - lane;   // an m-mer starts at row i iff 32 i <= m_limit
                     for (int r0 = 0; r0 < rounds; r0 += ILP) {
@@ -235,17 +168,18 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, LAYOUT == LAYOUT_LOCAL ?
                             constexpr int NR = ILP + 1;
                             const int m = k - LOCAL_W + 1, mbits = 2 * m;
                             const uint64_t mmask = (~0ull) >> (64 - mbits);
-                            uint64_t xs[ILP], rcs[ILP];
-                            uint64_t zs[NR];                  // mixed canonical m-mer | (a < b) << 63 | (a > b) << 62
+                            uint64_t cs[ILP];                 // canonical k-mers
+                            uint64_t zs[NR];                  // mixed canonical m-mer | (a < b) << 63 | (a > b) << 62 | (x <= rc) << 61
                             uint32_t AL[NR];
 #pragma unroll
                             for (int R = 0; R < NR; R++) {
                                 const int i = r0 + R;
-                                uint64_t x, rc;
+                                uint64_t c;
                                 uint32_t oh;
                                 if (R == 0 && have_carry) {           // warp-uniform: the previous group's tail row
-                                    x = carry_x; rc = carry_rc; zs[R] = carry_z; oh = carry_oh;
+                                    c = carry_c; zs[R] = carry_z; oh = carry_oh;
                                 } else {
+                                    uint64_t x, rc;
                                     const uint64_t hi = shfl64(W, i & 31), lo = shfl64(W, (i + 1) & 31);
                                     x = window64(hi, lo, 2 * lane) >> kshift;
                                     rc = revcomp2(x, k);
@@ -256,10 +190,12 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, LAYOUT == LAYOUT_LOCAL ?
                                     const uint64_t z = local_mix(lt ? a : b, mbits);
                                     oh = local_order(z, mbits);
                                     if (i > 31 || 32 * i > m_limit) oh = LOCAL_ORDER_MAX + 1;   // no m-mer here
-                                    zs[R] = z | ((uint64_t)lt << 63) | ((uint64_t)(!lt && a != b) << 62);
+                                    const bool kf = x <= rc;
+                                    c = kf ? x : rc;
+                                    zs[R] = z | ((uint64_t)lt << 63) | ((uint64_t)(!lt && a != b) << 62) | ((uint64_t)kf << 61);
                                 }
-                                if (R < ILP) { xs[R < ILP ? R : 0] = x; rcs[R < ILP ? R : 0] = rc; }
-                                if (R == NR - 1) { carry_x = x; carry_rc = rc; carry_z = zs[R]; carry_oh = oh; }
+                                if (R < ILP) cs[R < ILP ? R : 0] = c;
+                                if (R == NR - 1) { carry_c = c; carry_z = zs[R]; carry_oh = oh; }
                                 AL[R] = (oh << 8) | (uint32_t)(32 * R + lane);
                             }
                             have_carry = true;
@@ -279,16 +215,15 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, LAYOUT == LAYOUT_LOCAL ?
                             for (int j = 0; j < ILP; j++) {
                                 const int i = r0 + j;
                                 const bool valid = i < rounds && cb + 32 * i + lane < nk;
-                                const uint64_t x = xs[j], rc = rcs[j];
-                                const bool is_fwd = x <= rc;
-                                const uint64_t c = is_fwd ? x : rc;
+                                const uint64_t c = cs[j];
+                                const bool is_fwd = (zs[j] >> 61) & 1ull;
                                 const uint32_t pos = AL[j] & 255u;                            // 32 j + lane + offset
                                 const int src = (int)(pos & 31u);
                                 const uint64_t z0 = shfl64(zs[j], src), z1 = shfl64(zs[j + 1], src);
                                 const uint64_t zf = (pos >> 5) == (uint32_t)j ? z0 : z1;
                                 const int o_read = (int)((pos - (uint32_t)(32 * j + lane)) & 7u);
                                 uint32_t zq, line;
-                                local_divmod(zf & ((1ull << 62) - 1), (uint32_t)T.NL, T.nl_m32, T.nl_sh, zq, line);
+                                local_divmod(zf & ((1ull << 61) - 1), (uint32_t)T.NL, T.nl_m32, T.nl_sh, zq, line);
                                 const int o_c = is_fwd ? o_read : LOCAL_W - 1 - o_read;
                                 const bool f = (zf >> (is_fwd ? 63 : 62)) & 1ull;
                                 const uint32_t rest = local_rest(c, o_c, m);
@@ -316,7 +251,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, LAYOUT == LAYOUT_LOCAL ?
                                     if (label == NO_LABEL && sector_overflowed(sec[j]) && sector_overflowed(secb[j])) label = ovf_lookup(T, cc[j]);
                                     if (label >= p.n_targets) label = NO_LABEL;
                                 }
-                                account(label);
+                                hits.add(label, tkey, tcnt, lane);
                             }
                         } else {
 #pragma unroll
@@ -342,7 +277,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, LAYOUT == LAYOUT_LOCAL ?
                                         label = ovf_lookup(T, q[j] * T.M + ((uint64_t)lb[j] + T.lo));
                                     if (label >= p.n_targets) label = NO_LABEL;
                                 }
-                                account(label);
+                                hits.add(label, tkey, tcnt, lane);
                             }
                         }
                     }
@@ -351,76 +286,11 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, LAYOUT == LAYOUT_LOCAL ?
             }
 
         // ---- per-read result --------------------------------------------------
-        uint16_t* row = ROWS ? p.rows + (size_t)read * pitch : nullptr;
-        if (overflow) {
-            // exact dense fallback will overwrite; clear the table
-            tkey[lane] = EMPTY; tkey[lane + 32] = EMPTY; tcnt[lane] = 0; tcnt[lane + 32] = 0;
-            __syncwarp();
-            if (lane == 0) {
-                const uint32_t i = atomicAdd(&p.counters[COUNTER_DENSE], 1u);
-                if (i < p.dense_cap) p.dense_list[i] = read;
-            }
-            continue;
-        }
-        uint32_t v_sum, v_i1, v_h1, v_i2, v_h2;
-        if (!table_mode) {
-            const uint32_t h = __reduce_add_sync(0xFFFFFFFFu, my_same) & 0xFFFFu;
-            v_sum = h; v_i1 = h ? first_label + 1 : 0; v_h1 = h; v_i2 = 0; v_h2 = 0;
-            if (ROWS) {
-                for (int i = lane; i < pitch; i += 32) {
-                    uint16_t v = 0;
-                    if (h) v = i == 0 ? 1 : i == 1 ? (uint16_t)first_label : i == 2 ? (uint16_t)h : 0;
-                    row[i] = v;
-                }
-            }
-        } else {
-            // each lane owns slots lane and lane+32
-            const uint32_t l0 = tkey[lane], l1 = tkey[lane + 32];
-            const uint32_t h0 = l0 == EMPTY ? 0 : (tcnt[lane] & 0xFFFFu);
-            const uint32_t h1 = l1 == EMPTY ? 0 : (tcnt[lane + 32] & 0xFFFFu);
-            const uint32_t k0 = h0 ? (h0 << 16) | (0xFFFFu - l0) : 0;
-            const uint32_t k1 = h1 ? (h1 << 16) | (0xFFFFu - l1) : 0;
-            const uint32_t best = __reduce_max_sync(0xFFFFFFFFu, max(k0, k1));
-            const uint32_t e0 = k0 == best ? 0 : k0, e1 = k1 == best ? 0 : k1;
-            const uint32_t second = __reduce_max_sync(0xFFFFFFFFu, max(e0, e1));
-            v_sum = total & 0xFFFFu;
-            v_h1 = best >> 16; v_i1 = best ? (0xFFFFu - (best & 0xFFFFu)) + 1 : 0;
-            v_h2 = second >> 16; v_i2 = second ? (0xFFFFu - (second & 0xFFFFu)) + 1 : 0;
-            if (ROWS) {
-                uint16_t* srow = s_row[wib];
-                for (int i = lane; i < pitch; i += 32) srow[i] = 0;
-                __syncwarp();
-                // rank of each occupied slot = number of occupied slots with a smaller target
-                uint32_t r0 = 0, r1 = 0;
-                for (int s = 0; s < TSLOTS; s++) {
-                    const uint32_t ls = tkey[s];
-                    const bool occ = ls != EMPTY && (tcnt[s] & 0xFFFFu);
-                    r0 += occ && ls < l0;
-                    r1 += occ && ls < l1;
-                }
-                if (h0 && r0 < (uint32_t)p.row_pairs) { srow[1 + 2 * r0] = (uint16_t)l0; srow[2 + 2 * r0] = (uint16_t)h0; }
-                if (h1 && r1 < (uint32_t)p.row_pairs) { srow[1 + 2 * r1] = (uint16_t)l1; srow[2 + 2 * r1] = (uint16_t)h1; }
-                const uint32_t n = __popc(__ballot_sync(0xFFFFFFFFu, h0 != 0)) + __popc(__ballot_sync(0xFFFFFFFFu, h1 != 0));
-                if (lane == 0) {
-                    srow[0] = (uint16_t)n;
-                    if (n > (uint32_t)p.row_pairs) atomicAdd(&p.counters[COUNTER_TRUNC], 1u);
-                }
-                __syncwarp();
-                for (int i = lane; i < pitch; i += 32) row[i] = srow[i];
-            }
-            tkey[lane] = EMPTY; tkey[lane + 32] = EMPTY; tcnt[lane] = 0; tcnt[lane + 32] = 0;
-            __syncwarp();
-        }
-        if (p.final5 && lane < 5) {
-            const uint32_t v = lane == 0 ? v_sum : lane == 1 ? v_i1 : lane == 2 ? v_h1 : lane == 3 ? v_i2 : v_h2;
-            p.final5[(size_t)read * 5 + lane] = (uint16_t)v;
-        }
+        __syncwarp();
+        hits.finish<ROWS>(p.out, sptr[32] + sptr[34] - 1, tkey, tcnt, s_row[wib], lane);
         }   // reads of the chunk
+        flush_lookups();
     }       // chunks
-    // one atomic per warp
-    for (int o = 16; o; o >>= 1) my_lookups += __shfl_xor_sync(0xFFFFFFFFu, my_lookups, o);
-    if (lane == 0 && my_lookups)
-        atomicAdd(reinterpret_cast<unsigned long long*>(p.counters + COUNTER_LOOKUPS), my_lookups);
 }
 
 // Exact fallback for reads that hit more than TSLOTS distinct targets: one block
@@ -429,17 +299,17 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, LAYOUT == LAYOUT_LOCAL ?
 template <int LAYOUT>
 __global__ void __launch_bounds__(256) k_classify_dense(const ClassifyParams p, uint32_t* hist_all) {
     uint32_t* hist = hist_all + (size_t)blockIdx.x * p.n_targets;
-    const uint32_t n_list = min(p.counters[COUNTER_DENSE], p.dense_cap);
+    const uint32_t n_list = min(p.out.counters[COUNTER_DENSE], p.out.dense_cap);
     const int k = p.t.k;
-    const int pitch = 2 * p.row_pairs + 2;
     for (uint32_t li = blockIdx.x; li < n_list; li += gridDim.x) {
-        const uint32_t read = p.dense_list[li];
+        const uint32_t read = p.out.dense_list[li];
         uint32_t pos = p.reads_ptr[read];
         const uint32_t end = p.reads_ptr[read + 1];
         while (pos < end) {
-            const uint32_t L = p.cont[pos];
+            uint32_t L;
+            const uint32_t ncont = part_extent(p.cont[pos], pos + 1, end, L);      // clamped as in k_classify
             const uint16_t* c = p.cont + pos + 1;
-            pos += 1 + ((L + 7) >> 3);
+            pos += 1 + ncont;
             const int nk = (int)L - k + 1;
             for (int w = threadIdx.x; w < nk; w += blockDim.x) {
                 uint64_t x = 0;
@@ -452,27 +322,7 @@ __global__ void __launch_bounds__(256) k_classify_dense(const ClassifyParams p, 
             }
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
-            uint16_t best = 0, sbest = 0, ib = 0, isb = 0, sum = 0;
-            uint32_t n = 0;
-            uint16_t* row = p.rows ? p.rows + (size_t)read * pitch : nullptr;
-            if (row) for (int i = 0; i < pitch; i++) row[i] = 0;
-            for (uint32_t t = 0; t < p.n_targets; t++) {
-                const uint16_t h = (uint16_t)hist[t];
-                hist[t] = 0;
-                if (!h) continue;
-                if (h > best) { sbest = best; isb = ib; best = h; ib = (uint16_t)(t + 1); }
-                else if (h > sbest) { sbest = h; isb = (uint16_t)(t + 1); }
-                sum = (uint16_t)(sum + h);
-                if (row && n < (uint32_t)p.row_pairs) { row[1 + 2 * n] = (uint16_t)t; row[2 + 2 * n] = h; }
-                n++;
-            }
-            if (row) { row[0] = (uint16_t)n; if (n > (uint32_t)p.row_pairs) atomicAdd(&p.counters[COUNTER_TRUNC], 1u); }
-            if (p.final5) {
-                uint16_t* f = p.final5 + (size_t)read * 5;
-                f[0] = sum; f[1] = ib; f[2] = best; f[3] = isb; f[4] = sbest;
-            }
-        }
+        if (threadIdx.x == 0) dense_emit(hist, p.n_targets, read, p.out);
         __syncthreads();
     }
 }
@@ -664,9 +514,9 @@ int classify_launch(cuclark_db* db, const Scratch& sc, const uint32_t* d_ptr, co
     ClassifyParams p;
     p.t = db->view;
     p.reads_ptr = d_ptr; p.cont = d_cont; p.n_reads = (uint32_t)n_reads;
-    p.final5 = d_final; p.rows = d_rows; p.row_pairs = db->row_pairs;
     p.n_targets = (uint32_t)db->cfg.n_targets;
-    p.counters = sc.d_counters; p.dense_list = sc.d_dense_list; p.dense_cap = sc.dense_cap;
+    p.out.final5 = d_final; p.out.rows = d_rows; p.out.row_pairs = db->row_pairs;
+    p.out.counters = sc.d_counters; p.out.dense_list = sc.d_dense_list; p.out.dense_cap = sc.dense_cap;
     CK(cudaMemsetAsync(sc.d_counters, 0, N_COUNTERS * sizeof(uint32_t), st));
     if (n_reads == 0) return CUCLARK_OK;
     const int layout = db->view.layout;
@@ -690,6 +540,7 @@ int classify_launch(cuclark_db* db, const Scratch& sc, const uint32_t* d_ptr, co
     else k_classify_dense<LAYOUT_WIDE><<<db->dense_blocks, 256, 0, st>>>(p, db->d_dense_hist);
     CK(cudaGetLastError());
     CK(cudaEventRecord(db->dense_chain, st));
+    count_launches(2);
     return CUCLARK_OK;
 }
 
@@ -700,6 +551,7 @@ int merge_rows_launch(cuclark_db* db, const uint16_t* d_parts, int n_parts, size
     k_merge_rows<<<(unsigned)((n_reads + 255) / 256), 256, 0, st>>>(d_parts, n_parts, (uint32_t)n_reads, db->row_pairs,
                                                                    d_rows_out, d_final, db->scratch.d_counters);
     CK(cudaGetLastError());
+    count_launches(1);
     return CUCLARK_OK;
 }
 

@@ -11,7 +11,9 @@
 //
 // Differences, all in the direction of "less work for the caller":
 //  * -n / -b are accepted and echoed but only size the pipeline (chunks in flight);
-//  * -d N uses N GPUs read-partitioned (table replicated) instead of table-partitioned;
+//  * -d N (default: every GPU, as in the reference): a table that fits one GPU is loaded once, replicated over NVLink
+//    and the reads are dealt over the GPUs; a larger one is partitioned by bucket range as in the reference and the
+//    GPUs exchange k-mers and labels (csrc/route.cu);
 //  * a missing database is built on the GPU (cuclark_build_database) from FASTA targets, byte-identical
 //    to the reference's files; --tsk, spectrum/FASTQ targets and the 3rd targets column are not supported.
 #include <math.h>
@@ -23,6 +25,7 @@
 #include <algorithm>
 #include <iostream>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/cuclark_b200.h"
@@ -54,7 +57,7 @@ static void print_usage() {
          << "-R <fileResults>      results are written to <fileResults>.csv (or a list of names)\n"
          << "-n <numberofthreads>  host threads (chunks in flight per GPU)\n"
          << "-b <numberofbatches>  accepted for compatibility\n"
-         << "-d <numberofdevices>  number of GPUs (read-partitioned, table replicated)\n"
+         << "-d <numberofdevices>  number of GPUs (default: all; table replicated if it fits one GPU, partitioned otherwise)\n"
          << "-g <iteration>        gap of the cuCLARK-l database (part of its name; default 4)\n"
          << "-s <factor>           sampling factor when loading the database (cuCLARK only)\n"
          << "--tsk                 accepted for compatibility\n"
@@ -186,50 +189,119 @@ static void build_database(Cli& c, const string& base) {
     cerr << st.n_kmers_kept << " " << c.k << "-mers successfully stored in database." << endl;
 }
 
+static cuclark_db* create_handle(const Cli& c, int device, int shard, int n_shards) {
+    cuclark_config cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.k = (int)c.k;
+    cfg.htsize = HTSIZE;
+    cfg.n_targets = (int)(c.names.size() - 1);
+    cfg.device = device;
+    cfg.shard_index = shard;
+    cfg.shard_count = n_shards;
+    cuclark_db* db = nullptr;
+    const int rc = cuclark_create(&cfg, &db);
+    if (rc == CUCLARK_ERR_NO_DEVICE) {
+        cerr << "Not enough CUDA devices found: " << cuclark_last_error() << endl;      // src/CuClarkDB.cu:109-118
+        exit(1);
+    }
+    if (rc) die_lib("cuclark_create");
+    return db;
+}
+
+// .sz/.ky/.lb (or the table cache) into one handle
+static void load_into(Cli& c, cuclark_db* db, const string& base, bool announce) {
+    // --cache: <base>[.s<f>].b200 holds the table in its device layout; written after the first
+    // load from .sz/.ky/.lb, streamed back (no rebuild) while it still matches those files
+    const string cache = base + (c.sfactor > 1 ? ".s" + std::to_string(c.sfactor) : string()) + ".b200";
+    if (c.cache && valid_file(cache.c_str())) {
+        const int rc = cuclark_load_table(db, cache.c_str(), base.c_str(), (int)c.sfactor);
+        if (rc == CUCLARK_OK) { if (announce) cerr << "Table cache " << cache << " loaded." << endl; return; }
+        if (rc == CUCLARK_ERR_FORMAT || rc == CUCLARK_ERR_IO) cerr << "Ignoring table cache: " << cuclark_last_error() << endl;
+        else die_lib("cuclark_load_table");
+    }
+    const int rc = cuclark_load_db_files(db, base.c_str(), (int)c.sfactor);
+    if (rc == CUCLARK_ERR_IO) { cerr << cuclark_last_error() << endl << "Failed to find the database." << endl; exit(-1); }
+    if (rc) die_lib("cuclark_load_db_files");
+    if (c.cache && announce) {
+        if (cuclark_save_table(db, cache.c_str()) == CUCLARK_OK) cerr << "Table cache " << cache << " written." << endl;
+        else cerr << "Table cache not written: " << cuclark_last_error() << endl;
+    }
+}
+
+// CuClarkDB ctor + read (src/CuClarkDB.cu:85-208, 462-808). `-d` absent = every GPU found (src/main.cc:104,
+// src/CuClarkDB.cu:108-138). The reference ALWAYS partitions the table over the devices (:546-574). Here a table that
+// fits one device is loaded once and replicated over NVLink, the reads are dealt over the devices (no exchange at
+// all); a table that does not fit one device is partitioned by bucket range as in the reference, and the devices
+// exchange k-mers and labels (csrc/route.cu). CUCLARK_PARTITION_TABLE=1 forces the second mode.
 static void load_database(Cli& c) {
     const string base = db_name(c);
     bool present = true;
     for (const char* ext : {".sz", ".ky", ".lb"}) present = present && valid_file((base + ext).c_str());
     if (!present) build_database(c, base);
-    int n_dev = (int)c.devices;
-    if (n_dev == 0) n_dev = 1;
-    cerr << "Loading database [" << base << ".*] (s=" << c.sfactor << ")..." << endl;
-    for (int d = 0; d < n_dev; d++) {
+    int n_avail = 0;
+    uint64_t free0 = 0, total0 = 0;
+    if (cuclark_device_info(0, &n_avail, &free0, &total0) != CUCLARK_OK) {
+        cerr << "Not enough CUDA devices found: " << cuclark_last_error() << endl;          // src/CuClarkDB.cu:109-118
+        exit(1);
+    }
+    int n_dev = c.devices ? (int)c.devices : n_avail;
+    if (n_dev > n_avail) {
+        cerr << "Not enough CUDA devices found: " << n_avail << " of " << n_dev << " requested." << endl;   // :126-131
+        exit(1);
+    }
+    if (n_dev > 16) n_dev = 16;
+    // does the table fit one device? entries = bytes of .ky / key width (src/main.cc:278-316)
+    bool partition = getenv("CUCLARK_PARTITION_TABLE") != nullptr && n_dev > 1;
+    {
+        const size_t t_b = (size_t)(log((double)HTSIZE) / log(4.0));
+        const int kb = c.k <= t_b + 8 ? 2 : c.k <= t_b + 16 ? 4 : 8;
+        FILE* f = fopen((base + ".ky").c_str(), "rb");
+        uint64_t n_entries = 0;
+        if (f) { fseeko(f, 0, SEEK_END); n_entries = (uint64_t)ftello(f) / kb; fclose(f); }
         cuclark_config cfg;
         memset(&cfg, 0, sizeof cfg);
-        cfg.k = (int)c.k;
-        cfg.htsize = HTSIZE;
-        cfg.n_targets = (int)(c.names.size() - 1);
-        cfg.device = d;
-        cfg.shard_count = 1;
-        cuclark_db* db = nullptr;
-        int rc = cuclark_create(&cfg, &db);
-        if (rc == CUCLARK_ERR_NO_DEVICE) {
-            cerr << "Not enough CUDA devices found: " << cuclark_last_error() << endl;      // src/CuClarkDB.cu:109-118
-            exit(1);
-        }
-        if (rc) die_lib("cuclark_create");
-        // --cache: <base>[.s<f>].b200 holds the table in its device layout; written after the first
-        // load from .sz/.ky/.lb, streamed back (no rebuild) while it still matches those files
-        const string cache = base + (c.sfactor > 1 ? ".s" + std::to_string(c.sfactor) : string()) + ".b200";
-        bool from_cache = false;
-        if (c.cache && valid_file(cache.c_str())) {
-            rc = cuclark_load_table(db, cache.c_str(), base.c_str(), (int)c.sfactor);
-            if (rc == CUCLARK_OK) { from_cache = true; if (d == 0) cerr << "Table cache " << cache << " loaded." << endl; }
-            else if (rc == CUCLARK_ERR_FORMAT || rc == CUCLARK_ERR_IO) cerr << "Ignoring table cache: " << cuclark_last_error() << endl;
-            else die_lib("cuclark_load_table");
-        }
-        if (!from_cache) {
-            rc = cuclark_load_db_files(db, base.c_str(), (int)c.sfactor);
-            if (rc == CUCLARK_ERR_IO) { cerr << cuclark_last_error() << endl << "Failed to find the database." << endl; exit(-1); }
-            if (rc) die_lib("cuclark_load_db_files");
-            if (c.cache && d == 0) {
-                if (cuclark_save_table(db, cache.c_str()) == CUCLARK_OK) cerr << "Table cache " << cache << " written." << endl;
-                else cerr << "Table cache not written: " << cuclark_last_error() << endl;
+        cfg.k = (int)c.k; cfg.htsize = HTSIZE; cfg.n_targets = (int)(c.names.size() - 1); cfg.shard_count = 1;
+        cuclark_table_plan plan;
+        if (cuclark_plan_table(&cfg, n_entries / (c.sfactor > 1 ? c.sfactor : 1), &plan) == CUCLARK_OK) {
+            const double need = (double)plan.home_bytes * 1.10 + 3e9;      // + overflow table, build scratch, read buffers
+            if (need > (double)free0) {
+                if (n_dev < 2) {
+                    cerr << "The database needs about " << (size_t)(need / 1e9) << " GB of device memory, the device has "
+                         << (size_t)(free0 / 1e9) << " GB free: use more devices (-d)." << endl;
+                    exit(1);
+                }
+                partition = true;
             }
         }
-        c.dbs.push_back(db);
     }
+    cerr << "Loading database [" << base << ".*] (s=" << c.sfactor << ")..." << endl;
+    if (!partition) {
+        c.dbs.push_back(create_handle(c, 0, 0, 1));
+        load_into(c, c.dbs[0], base, true);
+        for (int d = 1; d < n_dev; d++) {                    // replicas: device-to-device copies of the built table
+            cuclark_db* db = create_handle(c, d, 0, 1);
+            if (cuclark_clone_table(c.dbs[0], db) != CUCLARK_OK) die_lib("cuclark_clone_table");
+            c.dbs.push_back(db);
+        }
+        if (n_dev > 1) cerr << "Using " << n_dev << " devices: table replicated, reads partitioned." << endl;
+        return;
+    }
+    // table-partitioned: shard d of n_dev on device d, loaded concurrently (the files are read through the page cache)
+    for (int d = 0; d < n_dev; d++) c.dbs.push_back(create_handle(c, d, d, n_dev));
+    vector<int> rcs(n_dev, 0);
+    vector<string> errs(n_dev);
+    vector<std::thread> th;
+    for (int d = 0; d < n_dev; d++)
+        th.emplace_back([&, d] {
+            rcs[d] = cuclark_load_db_files(c.dbs[d], base.c_str(), (int)c.sfactor);
+            if (rcs[d]) errs[d] = cuclark_last_error();
+        });
+    for (auto& t : th) t.join();
+    for (int d = 0; d < n_dev; d++) {
+        if (rcs[d] == CUCLARK_ERR_IO) { cerr << errs[d] << endl << "Failed to find the database." << endl; exit(-1); }
+        if (rcs[d]) { cerr << "CUERR '" << errs[d] << "' (cuclark_load_db_files, device " << d << ")" << endl; exit(1); }
+    }
+    cerr << "Using " << n_dev << " devices: table partitioned by bucket range, k-mers routed to their shard." << endl;
 }
 
 // src/CuCLARK_hh.hh:512-573

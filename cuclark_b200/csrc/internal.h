@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <mutex>
 #include <vector>
 
@@ -41,6 +42,8 @@ struct Batch {
 };
 
 struct TextPipe;   // stream.cu
+struct RouteCtx;   // route.cu
+constexpr int ROUTE_MAX_RANKS = CUCLARK_ROUTE_MAX_RANKS;
 
 }  // namespace cuclark
 
@@ -74,15 +77,23 @@ struct cuclark_db {
     bool batch_rows = false;
     // text pipeline (slots are allocated on first use and kept)
     cuclark::TextPipe* text_pipe = nullptr;
+    // table-partitioned mode by k-mer routing (route.cu)
+    cuclark::RouteCtx* route = nullptr;
 };
 
 namespace cuclark {
+
+// kernels launched by the hot path since the library was loaded (cuclark_kernel_launches): classify, merge,
+// text pipeline and k-mer routing launch sites count themselves; table builders and generators do not
+extern std::atomic<uint64_t> g_kernel_launches;
+inline void count_launches(int n) { g_kernel_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
 // table.cu
 int table_build_from_arrays(cuclark_db* db, const uint8_t* sz, const void* ky, const uint16_t* lb,
                             uint64_t n_entries_file, int sfactor, const char* base_path);
 int table_build_synthetic(cuclark_db* db, uint32_t seed, uint32_t n_targets, uint64_t genome_len, int light_gap);
 void table_free(cuclark_db* db);
+int table_clone(cuclark_db* src, cuclark_db* dst);
 void table_plan(const cuclark_config& cfg, uint64_t n_entries, cuclark_table_plan* out);
 int table_save(cuclark_db* db, const char* path);
 int table_load(cuclark_db* db, const char* path, const char* src_base, int sfactor);
@@ -99,6 +110,18 @@ int synth_fastq_launch(uint32_t seed, uint32_t genome_seed, uint32_t n_targets, 
                        size_t n_reads, int read_len, int pct_random, int sub_per_10k, uint8_t* d_text, cudaStream_t st);
 // stream.cu
 void text_pipe_free(cuclark_db* db);
+
+// route.cu
+int route_alloc(cuclark_db* db, int n_ranks, size_t max_containers);
+void route_free(cuclark_db* db);
+int route_export(cuclark_db* db, void* handle64, uint64_t* bytes);
+int route_import(cuclark_db* db, int peer_rank, const void* handle64);
+int route_connect(cuclark_db* const* dbs, int n);
+int route_scatter(cuclark_db* db, const uint32_t* d_ptr, const uint16_t* d_cont, size_t n_reads, size_t n_cont, cudaStream_t st);
+int route_probe(cuclark_db* db, cudaStream_t st);
+int route_gather(cuclark_db* db, const Scratch& sc, const uint32_t* d_ptr, const uint16_t* d_cont, size_t n_reads, size_t n_cont,
+                 uint16_t* d_final, uint16_t* d_rows, cudaStream_t st);
+int route_stats(cuclark_db* db, cuclark_route_stats* out);
 
 int gather_bench_launch(cuclark_db* db, uint64_t n_probes, int bytes_per_probe, int ilp, int iters, double* ms_out);
 

@@ -209,10 +209,25 @@ struct Job {
     bool timing = false;
     double t_phase[7] = {0, 0, 0, 0, 0, 0, 0};   // stage-in, h2d+index, pack, classify+csv, d2h, sink, slot allocation
 
+    // table-partitioned (routed) runs: the ranks work in lockstep rounds
+    int n_ranks = 0;
+    int bar_count = 0;
+    uint64_t bar_gen = 0;
+    int round_chunks = 0;            // ranks that got a chunk in the current round
+
     void fail(int code, const std::string& msg) {
         std::lock_guard<std::mutex> g(mu);
         if (!failed) { failed = true; rc = code; err = msg; }
         cv.notify_all();
+    }
+    // all n_ranks threads meet here; false if the job failed meanwhile (nobody is left waiting)
+    bool barrier() {
+        std::unique_lock<std::mutex> lk(mu);
+        if (failed) return false;
+        const uint64_t gen = bar_gen;
+        if (++bar_count == n_ranks) { bar_count = 0; bar_gen++; cv.notify_all(); return true; }
+        cv.wait(lk, [&] { return failed || bar_gen != gen; });
+        return !failed;
     }
 };
 
@@ -234,6 +249,26 @@ size_t record_boundary(const uint8_t* t, size_t n, size_t start, size_t want, bo
         if (l2[1] == '+') return p;
     }
     return start;      // no boundary inside the window: a record larger than a chunk
+}
+
+// First record start at or after `from` (or n): the end of a record that is larger than a chunk.
+size_t record_boundary_after(const uint8_t* t, size_t n, size_t from, bool fastq) {
+    for (size_t p = std::max<size_t>(from, 1); p < n; p++) {
+        if (t[p - 1] != '\n') {
+            const uint8_t* nl = (const uint8_t*)memchr(t + p, '\n', n - p);
+            if (!nl) return n;
+            p = (size_t)(nl - t);            // the loop increment moves to the line start
+            continue;
+        }
+        if (!fastq) { if (t[p] == '>') return p; continue; }
+        if (t[p] != '@') continue;
+        const uint8_t* l1 = (const uint8_t*)memchr(t + p, '\n', n - p);
+        if (!l1) return n;
+        const uint8_t* l2 = (const uint8_t*)memchr(l1 + 1, '\n', n - (size_t)(l1 + 1 - t));
+        if (!l2 || (size_t)(l2 + 1 - t) >= n) return n;
+        if (l2[1] == '+') return p;
+    }
+    return n;
 }
 
 #define JCK(call)                                                                                         \
@@ -324,17 +359,30 @@ void worker(Job& J, cuclark_db* db, TextSlot& S) {
             std::lock_guard<std::mutex> g(J.mu);
             if (J.failed || J.cursor >= J.n) return;
             start = J.cursor;
-            end = record_boundary(J.text, J.n, start, std::min(J.n, start + d.cap_bytes), J.fastq);
+            end = record_boundary(J.text, J.n, start, std::min(J.n, start + S.d.cap_bytes), J.fastq);
             if (end <= start) {
-                J.failed = true; J.rc = CUCLARK_ERR_ARG;
-                J.err = "a single record is larger than chunk_bytes (" + std::to_string(d.cap_bytes) + "); raise chunk_bytes";
-                J.cv.notify_all();
-                return;
+                // one record larger than the slot (the reference takes records of any size,
+                // src/CuCLARK_hh.hh:1377-1389): the chunk is that record alone and the slot grows to hold it
+                end = record_boundary_after(J.text, J.n, start + S.d.cap_bytes, J.fastq);
+                if (end - start > ((size_t)1 << 31)) {
+                    J.failed = true; J.rc = CUCLARK_ERR_ARG;
+                    J.err = "a single record of more than 2 GiB";
+                    J.cv.notify_all();
+                    return;
+                }
             }
             J.cursor = end;
             seq = J.next_seq++;
         }
         const uint32_t nb = (uint32_t)(end - start);
+        if (nb > S.d.cap_bytes) {
+            static std::mutex grow_mu;
+            std::lock_guard<std::mutex> g(grow_mu);
+            const bool stage = S.with_stage;
+            free_slot(S);
+            const int rc = alloc_slot(S, ((size_t)nb + (1u << 20)) & ~(size_t)255, tp->extended, tp->row_pairs, stage);
+            if (rc) { free_slot(S); J.fail(rc, cuclark_last_error()); return; }
+        }
         const uint8_t* src = J.text + start;
         pc.skip();
         if (!J.src_pinned) { memcpy(S.h_text, src, nb); src = S.h_text; }
@@ -437,6 +485,114 @@ void worker(Job& J, cuclark_db* db, TextSlot& S) {
     }
 }
 
+// Table-partitioned run (the reference's `-d N`, src/CuClarkDB.cu:546-574, 886-974): rank g = handle g holds shard g
+// and one slot. The ranks work in lockstep ROUNDS: each takes the next chunk of the input (in rank order, so the
+// CSV stays in file order), indexes and packs it, scatters its k-mers (route.cu); when all have, every shard probes
+// what is addressed to it; when all have, each rank gathers its labels, formats its CSV and hands it to the sink.
+void worker_routed(Job& J, cuclark_db* const* dbs, int g) {
+    cuclark_db* db = dbs[g];
+    const TextPipe* tp = db->text_pipe;
+    TextSlot& S = db->text_pipe->slots[0];
+    if (cudaSetDevice(db->cfg.device) != cudaSuccess) { J.fail(CUCLARK_ERR_CUDA, "cudaSetDevice failed"); return; }
+    if (S.stream && !J.src_pinned && !S.with_stage) free_slot(S);
+    if (!S.stream) {
+        static std::mutex alloc_mu;
+        std::lock_guard<std::mutex> lk(alloc_mu);
+        const int rc = alloc_slot(S, tp->chunk_bytes, tp->extended, tp->row_pairs, !J.src_pinned);
+        if (rc) { free_slot(S); J.fail(rc, cuclark_last_error()); return; }
+    }
+    const TextSlotDev& d = S.d;
+    const int k = db->cfg.k;
+    for (uint64_t round = 0;; round++) {
+        // ---- this rank's chunk of the round: cut in rank order
+        size_t start = 0, end = 0;
+        const uint64_t seq = round * (uint64_t)J.n_ranks + (uint64_t)g;
+        {
+            std::unique_lock<std::mutex> lk(J.mu);
+            J.cv.wait(lk, [&] { return J.failed || J.next_seq == seq; });
+            if (J.failed) return;
+            if (g == 0) J.round_chunks = 0;
+            if (J.cursor < J.n) {
+                start = J.cursor;
+                end = record_boundary(J.text, J.n, start, std::min(J.n, start + d.cap_bytes), J.fastq);
+                if (end <= start) {
+                    J.failed = true; J.rc = CUCLARK_ERR_ARG;
+                    J.err = "a single record is larger than chunk_bytes (" + std::to_string(d.cap_bytes) + "); raise chunk_bytes";
+                    J.cv.notify_all();
+                    return;
+                }
+                J.cursor = end;
+                J.round_chunks++;
+            }
+            J.next_seq++;
+            J.cv.notify_all();
+        }
+        const uint32_t nb = (uint32_t)(end - start);
+        uint32_t n_reads = 0;
+        uint64_t n_cont = 0;
+        if (nb) {
+            const uint8_t* src = J.text + start;
+            if (!J.src_pinned) { memcpy(S.h_text, src, nb); src = S.h_text; }
+            JCK(cudaMemcpyAsync(d.text, src, nb, cudaMemcpyHostToDevice, S.stream));
+            JRC(tp_index_launch(d, nb, J.fastq, S.stream));
+            JCK(cudaMemcpyAsync(S.h_info, d.info, sizeof(ChunkInfo), cudaMemcpyDeviceToHost, S.stream));
+            JCK(cudaStreamSynchronize(S.stream));
+            if (S.h_info->err) { J.fail(CUCLARK_ERR_NOMEM, tp_err_text(S.h_info->err)); return; }
+            n_reads = S.h_info->n_reads;
+            JRC(tp_pack_launch(d, nb, n_reads, k, S.stream));
+            JCK(cudaMemcpyAsync(S.h_info, d.info, sizeof(ChunkInfo), cudaMemcpyDeviceToHost, S.stream));
+            JCK(cudaStreamSynchronize(S.stream));
+            if (S.h_info->err) { J.fail(CUCLARK_ERR_NOMEM, tp_err_text(S.h_info->err)); return; }
+            n_cont = S.h_info->n_cont;
+        }
+        JRC(route_scatter(db, d.reads_ptr, d.cont, n_reads, n_cont, S.stream));
+        JCK(cudaStreamSynchronize(S.stream));
+        if (!J.barrier()) return;                            // every rank's k-mers are in its arena
+        bool any;
+        { std::lock_guard<std::mutex> lk(J.mu); any = J.round_chunks > 0; }
+        if (!any) return;                                    // the input is used up (all ranks see the same count)
+        JRC(route_probe(db, S.stream));
+        JCK(cudaStreamSynchronize(S.stream));
+        if (!J.barrier()) return;                            // every label is back with the rank that asked
+        JRC(route_gather(db, S.scratch, d.reads_ptr, d.cont, n_reads, n_cont, d.final5, J.extended ? d.rows : nullptr, S.stream));
+        JCK(cudaMemcpyAsync(S.h_counters, S.scratch.d_counters, N_COUNTERS * sizeof(uint32_t), cudaMemcpyDeviceToHost, S.stream));
+        JCK(cudaStreamSynchronize(S.stream));
+        if (S.h_counters[COUNTER_DENSE] > S.scratch.dense_cap) { J.fail(CUCLARK_ERR_NOMEM, "too many reads needed the dense fallback"); return; }
+        cuclark_route_stats rs;
+        JRC(route_stats(db, &rs));
+        if (rs.err) { J.fail(CUCLARK_ERR_NOMEM, "routing arena exhausted"); return; }
+        // ---- CSV of this rank's chunk, handed over in file order (chunk `seq`)
+        const size_t max_line = 39 + (J.extended ? 2 * (size_t)db->cfg.n_targets + 4 * (size_t)db->row_pairs : 0) + 64 +
+                                2 * (size_t)tp->names.max_len;
+        const uint32_t group = (uint32_t)std::min<size_t>(std::max<size_t>(d.cap_csv / max_line, 1), 0x7FFFFFFF);
+        if (!wait_turn(J, seq)) return;
+        for (uint32_t first = 0; first < n_reads; first += group) {
+            const uint32_t cnt = std::min(group, n_reads - first);
+            JRC(tp_csv_launch(d, tp->names, first, cnt, k, J.paired, J.extended, db->row_pairs, (uint32_t)db->cfg.n_targets, S.stream));
+            JCK(cudaMemcpyAsync(S.h_info, d.info, sizeof(ChunkInfo), cudaMemcpyDeviceToHost, S.stream));
+            JCK(cudaStreamSynchronize(S.stream));
+            if (S.h_info->err) { J.fail(CUCLARK_ERR_NOMEM, tp_err_text(S.h_info->err)); return; }
+            const size_t bytes = S.h_info->csv_bytes;
+            const uint64_t offset = J.out_off;
+            J.out_off += bytes;
+            if (!bytes) continue;
+            char* dst = S.h_csv;
+            if (J.out_buf) {
+                if (offset + bytes > J.out_cap) { J.fail(CUCLARK_ERR_NOMEM, "the output buffer is too small for the CSV"); return; }
+                if (J.out_pinned) dst = J.out_buf + offset;
+            }
+            JCK(cudaMemcpyAsync(dst, d.csv, bytes, cudaMemcpyDeviceToHost, S.stream));
+            JCK(cudaStreamSynchronize(S.stream));
+            if (J.out_buf && !J.out_pinned) memcpy(J.out_buf + offset, S.h_csv, bytes);
+            if (J.sink && J.sink(J.user, dst, bytes, offset) != 0) { J.fail(CUCLARK_ERR_IO, "the CSV sink reported an error"); return; }
+        }
+        J.n_reads += n_reads; J.n_cont += n_cont; J.n_chunks += nb ? 1 : 0;
+        J.lookups += rs.lookups;
+        J.dense += S.h_counters[COUNTER_DENSE]; J.trunc += S.h_counters[COUNTER_TRUNC];
+        end_turn(J);
+    }
+}
+
 int run_text(cuclark_db* const* dbs, int n_dbs, const uint8_t* text, size_t n, const cuclark_text_opts* o,
              cuclark_sink_fn sink, void* user, char* out_buf, size_t out_cap, cuclark_text_arrays* arrays,
              cuclark_text_stats* out) {
@@ -444,7 +600,11 @@ int run_text(cuclark_db* const* dbs, int n_dbs, const uint8_t* text, size_t n, c
     for (int i = 0; i < n_dbs; i++) {
         if (!dbs[i]) { set_error("null argument"); return CUCLARK_ERR_ARG; }
         if (!dbs[i]->d_table) { set_error("no database loaded"); return CUCLARK_ERR_STATE; }
-        if (dbs[i]->cfg.shard_count > 1) { set_error("the text pipeline needs the whole table on each device (read-partitioned mode)"); return CUCLARK_ERR_STATE; }
+        if (dbs[i]->cfg.shard_count > 1 && (dbs[i]->cfg.shard_count != n_dbs || dbs[i]->cfg.shard_index != i)) {
+            set_error("table-partitioned run: pass the %d shard handles in shard order (handle %d is shard %d of %d)", dbs[i]->cfg.shard_count, i,
+                      dbs[i]->cfg.shard_index, dbs[i]->cfg.shard_count);
+            return CUCLARK_ERR_STATE;
+        }
         if (dbs[i]->cfg.k != dbs[0]->cfg.k || dbs[i]->cfg.n_targets != dbs[0]->cfg.n_targets || dbs[i]->row_pairs != dbs[0]->row_pairs) {
             set_error("handles of a multi-device run must share k, n_targets and row_pairs");
             return CUCLARK_ERR_ARG;
@@ -463,11 +623,32 @@ int run_text(cuclark_db* const* dbs, int n_dbs, const uint8_t* text, size_t n, c
     chunk = (chunk + 255) & ~(size_t)255;
     int n_slots = o && o->n_slots > 0 ? o->n_slots : 4;
     n_slots = std::min(n_slots, 16);
+    const bool routed = dbs[0]->cfg.shard_count > 1;         // table-partitioned: one slot per rank, lockstep rounds
+    if (routed) {
+        if (arrays) { set_error("cuclark_text_debug needs the whole table on one device"); return CUCLARK_ERR_STATE; }
+        n_slots = 1;
+        if (!(o && o->chunk_bytes)) chunk = std::min<size_t>((size_t)32 << 20, std::max<size_t>((n / n_dbs + 4095) & ~(size_t)4095, (size_t)1 << 20));
+    }
     const bool extended = o && o->extended;
     for (int i = 0; i < n_dbs; i++) {
         CK(cudaSetDevice(dbs[i]->cfg.device));
         int rc = ensure_pipe(dbs[i], chunk, n_slots, extended || (arrays && arrays->rows), o ? o->target_names : nullptr);
         if (rc) return rc;
+    }
+    if (routed) {
+        // routing buffers for one chunk per rank (every k-mer starts in a data container: <= chunk/2 + slack containers)
+        const size_t cap_cont = chunk / 2 + 1024 + 8;
+        bool fresh = false;
+        for (int i = 0; i < n_dbs; i++) {
+            CK(cudaSetDevice(dbs[i]->cfg.device));
+            cuclark_route_stats rs;
+            if (!dbs[i]->route || route_stats(dbs[i], &rs) != CUCLARK_OK || rs.map_bytes != 8 * cap_cont * 4) {
+                int rc = route_alloc(dbs[i], n_dbs, cap_cont);
+                if (rc) return rc;
+                fresh = true;
+            }
+        }
+        if (fresh) { int rc = route_connect(dbs, n_dbs); if (rc) return rc; }
     }
     const auto t_setup = std::chrono::steady_clock::now();
     Job J;
@@ -501,6 +682,10 @@ int run_text(cuclark_db* const* dbs, int n_dbs, const uint8_t* text, size_t n, c
     const size_t max_threads = std::max<size_t>(std::min<size_t>(n_chunks_est, 2), n_chunks_est / 8);
     std::vector<std::thread> threads;
     size_t started = 0;
+    if (routed) {
+        J.n_ranks = n_dbs;
+        for (int i = 0; i < n_dbs; i++) threads.emplace_back([&J, dbs, i] { worker_routed(J, dbs, i); });
+    } else
     for (int s = 0; s < n_slots && started < max_threads; s++)
         for (int i = 0; i < n_dbs && started < max_threads; i++, started++) {
             cuclark_db* db = dbs[i];

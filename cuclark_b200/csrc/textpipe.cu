@@ -113,6 +113,7 @@ int scan_inplace(uint32_t* data, uint32_t n, uint32_t* tiles, size_t cap_tiles, 
     if (n_tiles) k_scan_apply<<<n_tiles, TPT, 0, st>>>(data, n, tiles, total64);
     else CK(cudaMemsetAsync(data, 0, 4, st));
     CK(cudaGetLastError());
+    count_launches(n_tiles ? 3 : 1);
     return CUCLARK_OK;
 }
 
@@ -285,6 +286,31 @@ __device__ __forceinline__ int nt_class(uint8_t c) {
 
 constexpr int PACK_WARPS = 8;
 
+// A part header is a uint16 (src/CuCLARK_hh.hh:1616-1708 sums the run length into one): a run of 65,536
+// nucleotides or more wraps it in the reference, whose kernel then reads data containers as headers
+// (undefined results). Here such a run becomes several parts of at most MAX_PART nt that OVERLAP by k-1 nt, so
+// that every k-mer of the run is still looked up exactly once (deviation Q8; oracle: orc_pack).
+constexpr uint32_t MAX_PART = 65535;
+
+// appends the `cnt` staged codes sbuf[fill .. fill+cnt) to the open part (run nucleotides so far, fill = run & 7
+// of them pending in sbuf[0..fill)): full containers go out, the remainder is moved to the front of sbuf
+__device__ __forceinline__ void pack_flush(uint16_t* out, uint32_t limit, uint32_t cc, uint32_t run, uint32_t cnt,
+                                           uint8_t* sbuf, int lane) {
+    const uint32_t fill = run & 7;
+    const uint32_t total = fill + cnt, full = total >> 3;
+    if ((uint32_t)lane < full) {
+        uint32_t w = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) w = (w << 2) | sbuf[8 * lane + i];
+        const uint32_t idx = cc + 1 + (run >> 3) + lane;
+        if (idx < limit) out[idx] = (uint16_t)w;
+    }
+    const uint8_t keep = (uint32_t)lane < (total & 7) ? sbuf[8 * full + lane] : 0;
+    __syncwarp();
+    if ((uint32_t)lane < (total & 7)) sbuf[lane] = keep;
+    __syncwarp();
+}
+
 // One warp packs (WRITE) or sizes (!WRITE) one read. Returns the number of containers.
 // `limit` (WRITE only) = containers this read owns: writes beyond it belong to parts that the
 // reference drops by rewinding its write index (:1699-1703) and must not touch the next read.
@@ -304,34 +330,30 @@ __device__ __forceinline__ uint32_t pack_read(const uint8_t* __restrict__ text, 
         int lo = 0;
         for (;;) {
             const uint32_t rest = lo < 32 ? (brk >> lo) << lo : 0u;
-            const int hi = rest ? __ffs(rest) - 1 : 32;
-            const uint32_t segmask = (hi >= 32 ? 0xFFFFFFFFu : ((1u << hi) - 1)) & ~((1u << lo) - 1);
-            const uint32_t nts = ntm & segmask;
-            const uint32_t cnt = __popc(nts);
+            int hi = rest ? __ffs(rest) - 1 : 32;
+            uint32_t segmask = (hi >= 32 ? 0xFFFFFFFFu : ((1u << hi) - 1)) & ~((1u << lo) - 1);
+            uint32_t nts = ntm & segmask;
+            uint32_t cnt = __popc(nts);
+            bool split = false;                              // the part is full: close it BEFORE lane hi
+            if (run + cnt > MAX_PART) {
+                cnt = MAX_PART - run;
+                hi = (int)__fns(nts, 0, (int)cnt + 1);       // the first nucleotide that does not fit
+                segmask &= (1u << hi) - 1;
+                nts &= segmask;
+                split = true;
+            }
             if (cnt) {
                 if (WRITE) {
-                    const uint32_t fill = run & 7;
-                    if ((nts >> lane) & 1) sbuf[fill + __popc(nts & lt)] = (uint8_t)cls;
+                    if ((nts >> lane) & 1) sbuf[(run & 7) + __popc(nts & lt)] = (uint8_t)cls;
                     __syncwarp();
-                    const uint32_t total = fill + cnt, full = total >> 3;
-                    if ((uint32_t)lane < full) {
-                        uint32_t w = 0;
-#pragma unroll
-                        for (int i = 0; i < 8; i++) w = (w << 2) | sbuf[8 * lane + i];
-                        const uint32_t idx = cc + 1 + (run >> 3) + lane;
-                        if (idx < limit) out[idx] = (uint16_t)w;
-                    }
-                    const uint8_t keep = (uint32_t)lane < (total & 7) ? sbuf[8 * full + lane] : 0;
-                    __syncwarp();
-                    if ((uint32_t)lane < (total & 7)) sbuf[lane] = keep;
-                    __syncwarp();
+                    pack_flush(out, limit, cc, run, cnt, sbuf, lane);
                 }
                 run += cnt;
             }
             if (hi >= 32) break;
-            // a break at lane hi closes the open part
+            // a break at lane hi (or a full part) closes the open part
             if (run) {
-                const uint32_t hdr = run & 0xFFFFu;              // uint16 header, wraps as the reference's does
+                const uint32_t hdr = run;                        // <= MAX_PART: fits the uint16 header
                 if (WRITE && lane == 0) {
                     const uint32_t fill = run & 7;
                     if (fill) {
@@ -342,11 +364,26 @@ __device__ __forceinline__ uint32_t pack_read(const uint8_t* __restrict__ text, 
                     }
                     if (hdr >= (uint32_t)k && cc < limit) out[cc] = (uint16_t)hdr;
                 }
+                if (WRITE) __syncwarp();
+                const uint32_t old_cc = cc;
                 if (hdr >= (uint32_t)k) cc += 1 + ((run + 7) >> 3);
                 run = 0;
-                if (WRITE) __syncwarp();
+                if (split) {
+                    // the next part starts with the last k-1 nucleotides of the one just closed
+                    const uint32_t ov = (uint32_t)k - 1;
+                    if (WRITE) {
+                        if ((uint32_t)lane < ov) {
+                            const uint32_t j = MAX_PART - ov + lane;
+                            const uint32_t idx = old_cc + 1 + (j >> 3);
+                            sbuf[lane] = idx < limit ? (uint8_t)((out[idx] >> (2 * (7 - (j & 7)))) & 3u) : 0;
+                        }
+                        __syncwarp();
+                        pack_flush(out, limit, cc, 0, ov, sbuf, lane);
+                    }
+                    run = ov;
+                }
             }
-            lo = hi + 1;
+            lo = split ? hi : hi + 1;
             if (lo >= 32) break;
         }
     }
@@ -492,6 +529,7 @@ int tp_index_launch(const TextSlotDev& s, uint32_t n, bool fastq, cudaStream_t s
         k_tp_records_fasta<<<grid, TPT, 0, st>>>(s.text, n, s.line_start, s.hdr_line, s.info, (uint32_t)s.cap_reads,
                                                  s.name_s, s.name_e, s.seq_s, s.seq_e, s.len);
     CK(cudaGetLastError());
+    count_launches(n_tiles ? 6 : 4);
     return CUCLARK_OK;
 }
 
@@ -505,6 +543,7 @@ int tp_pack_launch(const TextSlotDev& s, uint32_t n_bytes, uint32_t n_reads, int
     k_tp_check_cont<<<1, 1, 0, st>>>(s.info, s.cap_cont);
     if (grid) k_tp_pack<true><<<grid, PACK_WARPS * 32, 0, st>>>(s.text, n_reads, k, s.seq_s, s.seq_e, s.len, s.reads_ptr, s.cont, s.info);
     CK(cudaGetLastError());
+    count_launches(grid ? 3 : 1);
     return CUCLARK_OK;
 }
 
@@ -522,6 +561,7 @@ int tp_csv_launch(const TextSlotDev& s, const NameTable& names, uint32_t first, 
     k_tp_check_csv<<<1, 1, 0, st>>>(s.info, s.cap_csv);
     if (grid) k_tp_csv<true><<<grid, TPT, 0, st>>>(P);
     CK(cudaGetLastError());
+    count_launches(grid ? 3 : 1);
     return CUCLARK_OK;
 }
 

@@ -132,3 +132,35 @@ def reads_fastq(codes: np.ndarray, prefix: str = "r", first: int = 0, suffix: st
         out += (b"@" + prefix.encode() + str(first + r).encode() + suffix.encode() + b"\n"
                 + asc[r].tobytes() + b"\n+\n" + qual + b"\n")
     return bytes(out)
+
+
+def read_truth(seed: int, first: int, n_reads: int, read_len: int, n_targets: int, pct_random: int,
+               sub_per_10k: int = 0, k: int = 31, chunk: int = 1 << 20):
+    """Ground truth of reads ``first .. first+n_reads`` as the generators define them, without touching a database:
+    (target, clean) with target = source target (-1 for a random read) and clean = number of k-mer windows of the
+    read that hold no substituted base (= read_len-k+1 without substitutions). A target-specific k-mer database of
+    the same genomes classifies a sampled read as [clean, target+1, clean, 0, 0] and a random read as all zeros,
+    except for the handful of reads that touch a k-mer common to two targets or hit one by chance
+    (expected counts: bench.py). Works in chunks so that 10 M reads stay within a few hundred MB."""
+    target = np.empty(n_reads, np.int64)
+    clean = np.empty(n_reads, np.int64)
+    nk = read_len - k + 1
+    j = np.arange(read_len, dtype=U64)
+    for lo in range(0, n_reads, chunk):
+        hi = min(n_reads, lo + chunk)
+        i = np.arange(first + lo, first + hi, dtype=U64)
+        h1 = _key(TAG_READ, seed, i, U64(0))
+        is_random = (h1 % U64(100)) < U64(pct_random)
+        t = ((h1 >> U64(8)) % U64(n_targets)).astype(np.int64)
+        target[lo:hi] = np.where(is_random, -1, t)
+        if not sub_per_10k:
+            clean[lo:hi] = nk
+            continue
+        for a in range(lo, hi, 1 << 17):                    # (reads x read_len) hash matrix: smaller pieces
+            b = min(hi, a + (1 << 17))
+            ii = np.arange(first + a, first + b, dtype=U64)
+            sh = _key(TAG_SUB, seed, ii[:, None], j[None, :])
+            hit = ((sh % U64(10000)) < U64(sub_per_10k)).astype(np.int32)
+            cs = np.concatenate([np.zeros((b - a, 1), np.int32), np.cumsum(hit, axis=1, dtype=np.int32)], axis=1)
+            clean[a:b] = ((cs[:, k:] - cs[:, :nk]) == 0).sum(axis=1)
+    return target, clean

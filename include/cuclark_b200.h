@@ -91,6 +91,9 @@ typedef struct cuclark_stats {
 
 const char* cuclark_last_error(void);
 int cuclark_version(void);
+/* Kernels the hot path (classification, row merge, text pipeline, k-mer routing) has launched in this process since
+ * the library was loaded; bench.py reports the difference over its timed region as `gpu_launches`. */
+uint64_t cuclark_kernel_launches(void);
 
 /* CuClarkDB::CuClarkDB / ~CuClarkDB (src/CuClarkDB.cu:85-208, 215-260) */
 int cuclark_create(const cuclark_config* cfg, cuclark_db** out);
@@ -103,6 +106,13 @@ int cuclark_load_db_files(cuclark_db* db, const char* base, int sfactor);
 /* same from host arrays (sz: htsize bytes; ky: n_entries keys of key_bytes; lb) */
 int cuclark_load_db_arrays(cuclark_db* db, const uint8_t* sz, const void* ky, const uint16_t* lb,
                            uint64_t n_entries, int sfactor);
+/* The table of `src` copied device to device into `dst` (same configuration, another device): a replicated
+ * multi-GPU run reads and re-buckets the files once and sends the replicas over NVLink instead of rebuilding the
+ * table per device (the reference never replicates: src/CuClarkDB.cu:546-574). */
+int cuclark_clone_table(cuclark_db* src, cuclark_db* dst);
+/* CuClarkDB::CuClarkDB device enumeration (src/CuClarkDB.cu:108-138): number of CUDA devices and, for `device`,
+ * its free and total memory (each pointer may be NULL). CUCLARK_ERR_NO_DEVICE without a GPU. */
+int cuclark_device_info(int device, int* n_devices, uint64_t* free_bytes, uint64_t* total_bytes);
 /* Synthetic database built ON the device (bench.py at BASELINE sizes): all
  * canonical k-mers of n_targets seeded random genomes of genome_len bases
  * (stride 1 = every overlapping k-mer, as the full variant; the light variant
@@ -167,6 +177,50 @@ int cuclark_classify_device(cuclark_db* db, const uint32_t* d_reads_ptr, const u
  * Writes merged rows (may be NULL) and final results (may be NULL). */
 int cuclark_merge_rows_device(cuclark_db* db, const uint16_t* d_rows_parts, int n_parts, size_t n_reads,
                               uint16_t* d_rows_out, uint16_t* d_final5, void* stream);
+
+/* ---- table-partitioned mode by k-mer routing ---------------------------------------------------------
+ * The reference's multi-GPU mode (`-d N`) partitions the table by bucket range, copies every read batch to
+ * every device (src/CuClarkDB.cu:546-574, 886-895) and merges the per-device rows (:953-974): every device
+ * looks at every k-mer. Here rank g of N holds shard g (cfg.shard_index / shard_count, hashed layout) AND only
+ * its own reads: the canonical k-mers of the reads are bucketed by owner shard in g's HBM (scatter), every
+ * shard probes the k-mers addressed to it straight out of the peers' HBM over NVLink and stores the 2-byte
+ * labels straight back (probe), and g counts the labels per read (gather). The result equals the
+ * single-table result bit for bit. All ranks must pass a barrier between scatter and probe and between
+ * probe and gather (stream-ordered NCCL all-reduce between processes, events between the devices of one
+ * process — cuclark_classify_routed_device does it for the handles of one process). */
+#define CUCLARK_ROUTE_MAX_RANKS 16
+typedef struct cuclark_route_stats {
+    int n_ranks, rank;
+    uint64_t region_bytes;     /* arena + labels + block lists of this rank (peer-visible)               */
+    uint64_t map_bytes;        /* position map (local)                                                   */
+    uint64_t cap_blocks;       /* arena blocks of 256 entries                                            */
+    uint64_t lookups;          /* k-mers of this rank's reads in the last scatter                        */
+    uint64_t probed;           /* k-mers this shard probed for all ranks in the last probe               */
+    uint64_t blocks;           /* arena blocks used by the last scatter                                  */
+    uint64_t blocks_remote;    /* of which addressed to other ranks: x 256 x (8 + 2) bytes cross NVLink  */
+    uint32_t err;
+} cuclark_route_stats;
+/* Buffers for calls of up to max_containers containers (<= 2^28); the same value on every rank. */
+int cuclark_route_alloc(cuclark_db* db, int n_ranks, size_t max_containers);
+int cuclark_route_free(cuclark_db* db);
+/* One process per GPU: a 64-byte CUDA IPC handle of this rank's region, to be opened by the other ranks. */
+int cuclark_route_export(cuclark_db* db, void* handle64, uint64_t* region_bytes);
+int cuclark_route_import(cuclark_db* db, int peer_rank, const void* handle64);
+/* One process, N handles (in rank order; devices may differ or coincide): peer access + plain pointers. */
+int cuclark_route_connect(cuclark_db* const* dbs, int n);
+int cuclark_route_scatter(cuclark_db* db, const uint32_t* d_reads_ptr, const uint16_t* d_containers, size_t n_reads,
+                          size_t n_containers, void* stream);
+int cuclark_route_probe(cuclark_db* db, void* stream);
+int cuclark_route_gather(cuclark_db* db, const uint32_t* d_reads_ptr, const uint16_t* d_containers, size_t n_reads,
+                         size_t n_containers, uint16_t* d_final5, uint16_t* d_rows, void* stream);
+/* figures of the last scatter/probe; valid once the gather's stream is idle (cuclark_sync_stats) */
+int cuclark_route_get_stats(cuclark_db* db, cuclark_route_stats* out);
+/* The three steps for the N connected handles of ONE process, with the barriers between them (CUDA events across
+ * the devices): per rank its own device-resident reads and outputs. This is what the CLI's -d N runs when the
+ * table does not fit one device. */
+int cuclark_classify_routed_device(cuclark_db* const* dbs, int n, const uint32_t* const* d_reads_ptr,
+                                   const uint16_t* const* d_containers, const size_t* n_reads, const size_t* n_containers,
+                                   uint16_t* const* d_final5, uint16_t* const* d_rows);
 
 /* ---- database construction on the device -------------------------------------------------------
  * makeSpecificTargetSets + EHashtable::addElement + RemoveCommon + hTable::write

@@ -396,13 +396,19 @@ void orc_index_free(orc_index* ix) {
  * becomes a "part": one header container holding the run length followed by
  * ceil(len/8) containers, 8 nt each, MSB first, complement code, last one
  * left-aligned. Shorter runs leave nothing behind (the reference overwrites
- * them, :1646-1660 and :1699-1703). The header is a uint16 sum, so it wraps
- * for runs > 65535 nt exactly as the reference does.                           */
+ * them, :1646-1660 and :1699-1703).
+ * DEVIATION Q8: the header is a uint16 sum, so in the reference it
+ * wraps for runs of 65,536 nt or more and its kernel then reads data containers
+ * as headers (undefined results). Here — oracle and device packer alike — such a
+ * run becomes several parts of at most 65,535 nt that overlap by k-1 nt, so every
+ * k-mer of the run is still looked up exactly once.                             */
+#define ORC_MAX_PART 65535u
 size_t orc_pack_bound(const orc_index* ix, size_t first, size_t n) {
     size_t tot = 0;
     for (size_t i = first; i < first + n; i++) {
         size_t bytes = ix->seq_e[i] - ix->seq_s[i];
         tot += bytes / 8 + 2 + bytes / 16 + 2; /* generous: header per possible part */
+        tot += (bytes / ORC_MAX_PART + 1) * 8; /* overlap of split parts */
     }
     return tot + 8;
 }
@@ -420,13 +426,22 @@ size_t orc_pack(const uint8_t* map, const orc_index* ix, size_t first, size_t n,
             while (i < e && nt_rcode(map[i]) < 0) i++;
             if (i >= e) break;
             size_t hdr = cc++;
-            uint16_t runlen = 0, word = 0;
+            size_t runlen = 0;
+            size_t recent[32];                   /* byte positions of the last nucleotides */
+            uint16_t word = 0;
             unsigned fill = 0;
             while (i < e) {
                 int c = nt_rcode(map[i]);
                 if (c >= 0) {
+                    if (runlen == ORC_MAX_PART) {
+                        /* full part and the run goes on: the next part starts k-1 nucleotides back */
+                        i = recent[(runlen - (size_t)(k - 1)) & 31];
+                        break;
+                    }
+                    recent[runlen & 31] = i;
                     word = (uint16_t)((word << 2) | (unsigned)c);
-                    if (++fill == 8) { cont[cc++] = word; runlen = (uint16_t)(runlen + 8); fill = 0; word = 0; }
+                    if (++fill == 8) { cont[cc++] = word; fill = 0; word = 0; }
+                    runlen++;
                     i++;
                 } else if (map[i] == '\n') {
                     i++;
@@ -434,9 +449,9 @@ size_t orc_pack(const uint8_t* map, const orc_index* ix, size_t first, size_t n,
                     break;
                 }
             }
-            if (fill) { cont[cc++] = (uint16_t)(word << (2 * (8 - fill))); runlen = (uint16_t)(runlen + fill); }
-            if (runlen < k) cc = hdr;            /* drop the short run */
-            else cont[hdr] = runlen;
+            if (fill) cont[cc++] = (uint16_t)(word << (2 * (8 - fill)));
+            if (runlen < (size_t)k) cc = hdr;            /* drop the short run */
+            else cont[hdr] = (uint16_t)runlen;
         }
     }
     reads_ptr[n] = (uint32_t)cc;

@@ -98,7 +98,8 @@ def test_ctypes_structs_match_the_header(tmp_path):
     import subprocess
     pairs = [("cuclark_config", api.Config), ("cuclark_stats", api.Stats), ("cuclark_table_plan", api.TablePlan),
              ("cuclark_build_opts", api.BuildOpts), ("cuclark_build_stats", api.BuildStats),
-             ("cuclark_text_opts", api.TextOpts), ("cuclark_text_stats", api.TextStats), ("cuclark_text_arrays", api.TextArrays)]
+             ("cuclark_text_opts", api.TextOpts), ("cuclark_text_stats", api.TextStats), ("cuclark_text_arrays", api.TextArrays),
+             ("cuclark_route_stats", api.RouteStats)]
     src = tmp_path / "sizes.c"
     src.write_text('#include <stdio.h>\n#include "cuclark_b200.h"\nint main(void) {\n' +
                    "".join(f'  printf("{c} %zu\\n", sizeof({c}));\n' for c, _ in pairs) + "  return 0;\n}\n")

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 from oracle import dbtools
-from oracle.binding import RefLookup
+from oracle.binding import HTSIZE_LIGHT, RefLookup
 
 
 @pytest.mark.parametrize("name", ["light_small", "light_c1"])
@@ -88,4 +88,35 @@ def test_port_sampling_equals_reference(oracle, light_small, tmp_path, sfactor):
     a, ha = db.query(light_small.kmers)
     b, hb = ref.query(light_small.kmers)
     assert np.array_equal(a, b) and 0 < ha < light_small.kmers.size
+    ref.close()
+
+
+@pytest.mark.parametrize("k", [19, 30, 32])
+def test_port_lookup_equals_reference_find_other_key_widths(oracle, tmp_path, k):
+    """uint16 (k=19) and uint64 (k=30, 32) `.ky` elements: EHashtable<uint16_t/uint64_t, rElement> of the
+    reference (the T16/T64 branches of src/main.cc:278-316) against the port, every DB k-mer in both
+    orientations + random k-mers."""
+    from cuclark_b200 import synth
+    from oracle.binding import key_bytes_for
+    try:
+        ref = RefLookup(light=True)
+    except FileNotFoundError:
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    targets = [synth.genome_codes(40 + k, t, 0, 20_000) for t in range(5)]
+    kmers, labels = dbtools.build_entries(targets, k, 0)
+    kb = key_bytes_for(k, HTSIZE_LIGHT)
+    assert kb == (2 if k == 19 else 8)
+    sz, ky, lb = dbtools.entries_to_arrays(kmers, labels, HTSIZE_LIGHT, kb)
+    base = str(tmp_path / "db")
+    dbtools.write_db_files(base, sz, ky, lb)
+    ref.open(base, k)
+    db = oracle.db_load(base, HTSIZE_LIGHT, k)
+    rng = np.random.default_rng(k)
+    hi = (1 << 64) - 1 if k == 32 else (1 << (2 * k)) - 1
+    probe = np.concatenate([kmers, dbtools.revcomp_codes(kmers, k),
+                            rng.integers(0, hi, 100_000, dtype=np.uint64, endpoint=True)])
+    a, ha = db.query(probe, 4)
+    b, hb = ref.query(probe, 4)
+    assert ha == hb and np.array_equal(a, b)
+    assert ha >= 2 * kmers.size
     ref.close()
