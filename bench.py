@@ -67,6 +67,9 @@ def parse():
     ap.add_argument("--layout", type=int, default=int(os.environ.get("CUCLARK_BENCH_LAYOUT", 0)),
                     help="device table layout: 0 auto, 1 narrow, 2 wide, 3 local (minimizer-addressed lines)")
     ap.add_argument("--load", type=float, default=0.0, help="entries per bucket (0 = the layout's default)")
+    ap.add_argument("--no-table-mode", action="store_true", help="N > 1: skip the table-partitioned sub-records")
+    ap.add_argument("--c5-targets", type=int, default=11000,
+                    help="N > 1: targets of the configs[4] table (44 G entries, ~600 GB) measured when the shards fit; 0 = skip")
     ap.add_argument("--mode", default="read", choices=["read", "table"],
                     help="multi-GPU mode: read-partitioned/replicated table, or table-partitioned + NCCL row exchange")
     return ap.parse_args()
@@ -278,6 +281,91 @@ def workload_config(args, world):
                      "table-partitioned, rows exchanged over NCCL all-to-all" if args.mode == "table"
                      else "read-partitioned, replicated table"),
             "l2_policy": "inputs larger than L2 (packed reads 400 MB, table >> 126 MB); no flush needed"}
+
+
+def run_table_mode(args, rank, world, local, targets, d_ptr, d_cont, n, ts, ref_final=None, steps=None):
+    """Table-partitioned run of the SAME reads: rank r holds shard r of the table (hashed sectors) and its own reads;
+    k-mers travel to their shard and labels come back over NVLink inside the probe kernel (csrc/route.cu), with two
+    stream-ordered NCCL all-reduces of one float as the barriers between scatter | probe | gather."""
+    import torch
+    import torch.distributed as dist
+    from cuclark_b200 import synth
+    from cuclark_b200.api import CuClarkDB, HTSIZE_FULL
+    steps = steps or args.steps
+    per = 1 + (READ_LEN + 7) // 8
+    stream = ts.cuda_stream
+    g = CuClarkDB(K, targets, htsize=HTSIZE_FULL, device=local, shard=(rank, world))
+    t0 = time.time()
+    g.build_synthetic(DB_SEED, targets, GENOME_LEN, 0)
+    build_s = time.time() - t0
+    st = g.stats()
+    g.route_alloc(world, n * per)
+    mine = g.route_export()
+    handles = [None] * world
+    dist.all_gather_object(handles, mine)
+    for r in range(world):
+        if r != rank:
+            g.route_import(r, handles[r])
+    d_final = torch.zeros(n * 5, dtype=torch.int16, device="cuda")
+    tok = torch.zeros(1, device="cuda")
+    torch.cuda.synchronize()
+    dist.barrier()
+
+    def step():
+        with torch.cuda.stream(ts):
+            g.route_scatter(d_ptr.data_ptr(), d_cont.data_ptr(), n, n * per, stream)
+            dist.all_reduce(tok)                      # every rank's k-mers are in its arena
+            g.route_probe(stream)
+            dist.all_reduce(tok)                      # every label is back with the rank that asked
+            g.route_gather(d_ptr.data_ptr(), d_cont.data_ptr(), n, n * per, d_final.data_ptr(), 0, stream)
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize(); dist.barrier()
+    from cuclark_b200 import api as _api
+    l0 = _api.kernel_launches()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev[0].record(ts)
+    for _ in range(steps):
+        step()
+    ev[1].record(ts)
+    launches = _api.kernel_launches() - l0
+    torch.cuda.synchronize(); dist.barrier()
+    ms = ev[0].elapsed_time(ev[1]) / steps
+    g.stats(sync_stream=stream, sync=True)
+    rs = g.route_stats()
+    f = d_final.view(n, 5).cpu().numpy().view(np.uint16)
+    same = bool(np.array_equal(f, ref_final)) if ref_final is not None else None
+    # ground truth from the generator (as for the read-partitioned rows)
+    n_chk = n if not args.sub_per_10k else min(n, 1_000_000)
+    tgt, clean = synth.read_truth(READ_SEED, rank * n, n_chk, READ_LEN, targets, args.pct_random, args.sub_per_10k, K)
+    exp = np.zeros((n_chk, 5), np.uint16)
+    smp = (tgt >= 0) & (clean > 0)
+    exp[smp, 0] = clean[smp]; exp[smp, 1] = tgt[smp] + 1; exp[smp, 2] = clean[smp]
+    bad = int(((f[:n_chk] != exp).any(axis=1)).sum())
+    n_entries_all = float(targets) * (GENOME_LEN - K + 1)
+    bound = int(10 + n_chk * READ_LEN * 4 * n_entries_all / 4.0 ** K + n_chk * 120 * 2 * n_entries_all / 4.0 ** K)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    c = torch.tensor([float(rs["lookups"]), float(rs["probed"]), float(rs["blocks_remote"]), float(st["table_bytes"]),
+                      float(bad), float(0 if same in (True, None) else 1), float(rs["err"])], dtype=torch.float64, device="cuda")
+    dist.all_reduce(c, op=dist.ReduceOp.SUM)
+    lookups_all, probed_all, blocks_remote, table_bytes, bad_all, differ, err = c.tolist()
+    g.close()
+    del d_final
+    torch.cuda.empty_cache()
+    ms_max = t.item()
+    return {"value": lookups_all / (ms_max * 1e-3), "unit": "lookups/s", "ms_per_step": ms_max, "steps": steps,
+            "targets": targets, "table_bytes_all_shards": table_bytes, "table_bytes_per_gpu": table_bytes / world,
+            "layout": {1: "narrow", 2: "wide", 3: "local"}.get(st["layout"]), "shard_build_s": build_s,
+            "lookups_per_step": lookups_all, "probed_per_step": probed_all,
+            "nvlink_bytes_per_lookup": blocks_remote * 256 * 10 / max(lookups_all, 1.0),
+            "routing_buffers_bytes_per_gpu": rs["region_bytes"] + rs["map_bytes"],
+            "rows_equal_read_partitioned": (differ == 0) if ref_final is not None else None,
+            "rows_equal_ground_truth": bool(bad_all <= bound * world), "ground_truth_mismatches": int(bad_all),
+            "gpu_launches_per_rank": launches, "route_err": int(err),
+            "path": "reads partitioned, table partitioned by bucket range; k_route_scatter | all-reduce | k_route_probe "
+                    "(peer loads of k-mers, peer stores of labels over NVLink) | all-reduce | k_route_gather"}
 
 
 # ---------------------------------------------------------------- GPU arm
@@ -509,6 +597,26 @@ def run_b200(args):
     total_ms_max, e2e_s_max, text_s_max, h2d_s_max = t.tolist()
     lookups_all, reads_all = cnt.tolist()
 
+    # ---- the same reads through the table-partitioned path (N > 1) -------------------
+    table_records = {}
+    if world > 1 and not table_mode and not args.no_table_mode:
+        g.close()
+        torch.cuda.empty_cache()
+        table_records["table_mode"] = run_table_mode(args, rank, world, local, T, d_ptr, d_cont, n, ts, ref_final=f)
+        # BASELINE configs[4]: a table that exceeds one GPU (11,000 targets = 44 G entries, ~600 GB over the shards)
+        free_b = torch.cuda.mem_get_info()[0]
+        c5_targets = args.c5_targets
+        need_per_gpu = c5_targets * (GENOME_LEN - K + 1) / 2.6 * 32 * 1.06 / world + 30e9
+        if c5_targets and need_per_gpu < free_b:
+            n5 = min(n, 5_000_000)
+            gen = CuClarkDB(K, c5_targets, htsize=HTSIZE_FULL, device=local)          # a handle without a table: generator only
+            gen.synth_reads_device(READ_SEED, DB_SEED, c5_targets, GENOME_LEN, rank * n5, n5, READ_LEN, args.pct_random,
+                                   args.sub_per_10k, d_ptr.data_ptr(), d_cont.data_ptr(), stream)
+            gen.stats(sync_stream=stream, sync=True)
+            gen.close()
+            table_records["table_mode_config5"] = run_table_mode(args, rank, world, local, c5_targets, d_ptr, d_cont, n5, ts,
+                                                                 steps=max(2, args.steps // 2))
+
     if rank == 0:
         peak, peak_src = measured_peaks()
         kernel_ms = float(np.mean(step_ms))
@@ -537,6 +645,7 @@ def run_b200(args):
                                   "reads_with_all_kmers_hit_frac": full_hits,
                                   "final_rows_sha1_rank0": final_sha1, **gt},
         }
+        line.update(table_records)
         if e2e_text:
             line["e2e"] = {"value": lookups_all / text_s_max, "unit": "lookups/s", "reads_per_s": reads_all / text_s_max,
                            "h2d_bytes_per_step": e2e_text["h2d"], "d2h_bytes_per_step": e2e_text["d2h"],

@@ -150,6 +150,13 @@ def load_library():
     lib.cuclark_save_table.argtypes = [vp, C.c_char_p]
     lib.cuclark_load_table.argtypes = [vp, C.c_char_p, C.c_char_p, ci]
     lib.cuclark_classify_file_multi.argtypes = [P(vp), ci, C.c_char_p, C.c_char_p, P(TextOpts), P(TextStats)]
+    if not hasattr(lib, "cuclark_route_alloc"):         # (variant build from before the routing entry points)
+        _lib = lib
+        for name in ABI_SYMBOLS:
+            fn = getattr(lib, name, None)
+            if fn is not None and name != "cuclark_last_error":
+                fn.restype = ci
+        return lib
     lib.cuclark_clone_table.argtypes = [vp, vp]
     lib.cuclark_device_info.argtypes = [ci, P(ci), P(u64), P(u64)]
     lib.cuclark_route_alloc.argtypes = [vp, ci, sz]
@@ -162,11 +169,17 @@ def load_library():
     lib.cuclark_route_gather.argtypes = [vp, vp, vp, sz, sz, vp, vp, vp]
     lib.cuclark_route_get_stats.argtypes = [vp, P(RouteStats)]
     lib.cuclark_classify_routed_device.argtypes = [P(vp), ci, P(vp), P(vp), P(sz), P(sz), P(vp), P(vp)]
+    variant = bool(os.environ.get("CUCLARK_LIB"))       # an older build for A/B timing may lack the newest entry points
     for name in ABI_SYMBOLS:
-        fn = getattr(lib, name)
+        fn = getattr(lib, name, None)
+        if fn is None:
+            if variant:
+                continue
+            raise AttributeError(f"{name} is declared in include/cuclark_b200.h but not exported by {path}")
         if name not in ("cuclark_last_error", "cuclark_kernel_launches"):
             fn.restype = ci
-    lib.cuclark_kernel_launches.restype = u64
+    if hasattr(lib, "cuclark_kernel_launches"):
+        lib.cuclark_kernel_launches.restype = u64
     _lib = lib
     return lib
 
@@ -177,7 +190,8 @@ class TablePlan(C.Structure):
 
 def kernel_launches() -> int:
     """Hot-path kernels launched by the library in this process so far (cuclark_kernel_launches)."""
-    return int(load_library().cuclark_kernel_launches())
+    lib = load_library()
+    return int(lib.cuclark_kernel_launches()) if hasattr(lib, "cuclark_kernel_launches") else 0
 
 
 def plan_table(k: int, n_entries: int, htsize: int = HTSIZE_FULL, n_targets: int = 1, shard=(0, 1), bucket_load: float = 0.0,

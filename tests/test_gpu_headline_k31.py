@@ -96,9 +96,11 @@ def _reads_from(targets, rng, n, k):
 @pytest.mark.slow
 @pytest.mark.parametrize("k,htsize,layouts", [(32, HTSIZE_FULL, (0, 2)), (30, HTSIZE_LIGHT, (0, 1, 2, 3)),
                                               (29, HTSIZE_LIGHT, (0, 3))])
-def test_uint64_keys(oracle, k, htsize, layouts):
+def test_uint64_keys(oracle, k, htsize, layouts, monkeypatch):
     """8-byte .ky elements: k=32 on the full HTSIZE is the reference's T64 instantiation
-    (CuClarkDB<uint64_t>, src/main.cc:278-316); k=29/30 on the light HTSIZE have 8-byte keys too."""
+    (CuClarkDB<uint64_t>, src/main.cc:278-316); k=29/30 on the light HTSIZE have 8-byte keys too.
+    (LOCAL at k=30 is a 17 GB table of 2^27 lines whatever it holds: forced as in the k=31 test.)"""
+    monkeypatch.setenv("CUCLARK_ALLOW_SPARSE_TABLE", "1")
     targets, kmers, labels, (sz, ky, lb), kb = _small_case(k, htsize)
     assert kb == 8 and ky.dtype == np.uint64
     odb = oracle.db_from_arrays(htsize, k, sz, ky, lb)
