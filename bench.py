@@ -311,13 +311,24 @@ def run_table_mode(args, rank, world, local, targets, d_ptr, d_cont, n, ts, ref_
     torch.cuda.synchronize()
     dist.barrier()
 
-    def step():
+    def step(marks=None):
+        def mark():
+            if marks is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record(ts)
+                marks.append(e)
         with torch.cuda.stream(ts):
+            mark()
             g.route_scatter(d_ptr.data_ptr(), d_cont.data_ptr(), n, n * per, stream)
+            mark()
             dist.all_reduce(tok)                      # every rank's k-mers are in its arena
+            mark()
             g.route_probe(stream)
+            mark()
             dist.all_reduce(tok)                      # every label is back with the rank that asked
+            mark()
             g.route_gather(d_ptr.data_ptr(), d_cont.data_ptr(), n, n * per, d_final.data_ptr(), 0, stream)
+            mark()
 
     for _ in range(3):
         step()
@@ -332,6 +343,12 @@ def run_table_mode(args, rank, world, local, targets, d_ptr, d_cont, n, ts, ref_
     launches = _api.kernel_launches() - l0
     torch.cuda.synchronize(); dist.barrier()
     ms = ev[0].elapsed_time(ev[1]) / steps
+    # one more step with an event after every phase (this rank's view; the waits include the slower ranks)
+    marks = []
+    step(marks)
+    torch.cuda.synchronize(); dist.barrier()
+    names = ["scatter", "wait_all_scattered", "probe", "wait_all_probed", "gather"]
+    phase_ms = {nm: marks[i].elapsed_time(marks[i + 1]) for i, nm in enumerate(names)}
     g.stats(sync_stream=stream, sync=True)
     rs = g.route_stats()
     f = d_final.view(n, 5).cpu().numpy().view(np.uint16)
@@ -363,7 +380,7 @@ def run_table_mode(args, rank, world, local, targets, d_ptr, d_cont, n, ts, ref_
             "routing_buffers_bytes_per_gpu": rs["region_bytes"] + rs["map_bytes"],
             "rows_equal_read_partitioned": (differ == 0) if ref_final is not None else None,
             "rows_equal_ground_truth": bool(bad_all <= bound * world), "ground_truth_mismatches": int(bad_all),
-            "gpu_launches_per_rank": launches, "route_err": int(err),
+            "gpu_launches_per_rank": launches, "route_err": int(err), "phase_ms_rank0": phase_ms,
             "path": "reads partitioned, table partitioned by bucket range; k_route_scatter | all-reduce | k_route_probe "
                     "(peer loads of k-mers, peer stores of labels over NVLink) | all-reduce | k_route_gather"}
 

@@ -58,6 +58,7 @@ struct cuclark_db {
     uint64_t n_entries = 0, n_spilled = 0, n_spill_buckets = 0;
     int src_sfactor = 1;               // -s the table was built with, and the sizes of its source files
     uint64_t src_bytes[3] = {0, 0, 0}; //   (.sz/.ky/.lb; 0 when built from arrays or synthetic): table cache header
+    uint64_t src_mtime_ns[3] = {0, 0, 0};
     // classify scratch (one-shot calls; batches carry their own)
     cuclark::Scratch scratch;
     uint32_t* d_dense_hist = nullptr;  // dense_blocks * n_targets, shared: dense kernels are

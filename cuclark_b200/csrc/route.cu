@@ -39,6 +39,7 @@ constexpr uint64_t SENTINEL = ~0ull;              // unused arena entry (never a
 constexpr uint16_t LABEL_NONE = 0xFFFF;
 constexpr int R_WARPS = 8;
 constexpr int R_READS_PER_CHUNK = 31;
+constexpr int SCATTER_BLOCKS_PER_SM = 4;
 constexpr uint32_t ROUTE_ERR_ARENA = 1u;
 
 // Head of a rank's region; the peers read nblk[] (how many blocks are addressed to them).
@@ -102,7 +103,7 @@ __device__ __forceinline__ int owner_of(const ScatterParams& p, uint64_t b) {
 }
 
 // ---- scatter: k-mers of this rank's reads into per-owner blocks of the local arena -------------------------
-__global__ void __launch_bounds__(R_WARPS * 32, 2) k_route_scatter(const ScatterParams p) {
+__global__ void __launch_bounds__(R_WARPS * 32, SCATTER_BLOCKS_PER_SM) k_route_scatter(const ScatterParams p) {
     __shared__ uint32_t s_base[R_WARPS][ROUTE_MAX_RANKS];     // arena index of the owner's open block
     __shared__ uint32_t s_used[R_WARPS][ROUTE_MAX_RANKS];     // entries used in it (BLK = none open)
     __shared__ uint32_t s_ptr[R_WARPS][32];
@@ -396,7 +397,7 @@ int route_alloc(cuclark_db* db, int n_ranks, size_t max_containers) {
     r->n_ranks = n_ranks; r->rank = db->cfg.shard_index; r->cap_cont = max_containers; r->sm_count = db->sm_count;
     // every k-mer starts at a nucleotide of a data container: at most 8 per container. On top, each warp of the
     // scatter kernel leaves at most one open block per owner and wastes < 32 entries per block it closes.
-    const uint64_t warps = (uint64_t)db->sm_count * 2 * R_WARPS;
+    const uint64_t warps = (uint64_t)db->sm_count * SCATTER_BLOCKS_PER_SM * R_WARPS;
     const uint64_t entries = 8ull * max_containers;
     const uint64_t blocks = (entries + (BLK - 32) - 1) / (BLK - 32) + warps * n_ranks + 64;
     if (blocks * BLK >= 0xFFFFFFFFull) { delete r; set_error("routing arena exceeds 2^32 entries: lower max_containers"); return CUCLARK_ERR_ARG; }
@@ -487,7 +488,7 @@ int route_scatter(cuclark_db* db, const uint32_t* d_ptr, const uint16_t* d_cont,
     p.mine = region_view(r->region, r->n_ranks, r->cap_blocks);
     p.cap_blocks = r->cap_blocks;
     p.pos_of = r->pos_of;
-    const int blocks = (int)std::min<size_t>((n_reads + R_WARPS - 1) / R_WARPS, (size_t)r->sm_count * 2);
+    const int blocks = (int)std::min<size_t>((n_reads + R_WARPS - 1) / R_WARPS, (size_t)r->sm_count * SCATTER_BLOCKS_PER_SM);
     k_route_scatter<<<blocks, R_WARPS * 32, 0, st>>>(p);
     CK(cudaGetLastError());
     count_launches(1);

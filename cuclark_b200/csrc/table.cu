@@ -724,7 +724,7 @@ int table_clone(cuclark_db* src, cuclark_db* dst) {
     dst->view.buckets = t; dst->view.ovf = o;
     dst->n_entries = src->n_entries; dst->n_spilled = src->n_spilled; dst->n_spill_buckets = src->n_spill_buckets;
     dst->src_sfactor = src->src_sfactor;
-    for (int i = 0; i < 3; i++) dst->src_bytes[i] = src->src_bytes[i];
+    for (int i = 0; i < 3; i++) { dst->src_bytes[i] = src->src_bytes[i]; dst->src_mtime_ns[i] = src->src_mtime_ns[i]; }
     return CUCLARK_OK;
 }
 
@@ -737,10 +737,13 @@ void table_free(cuclark_db* db) {
     db->n_entries = db->n_spilled = db->n_spill_buckets = 0;
     db->src_sfactor = 1;
     db->src_bytes[0] = db->src_bytes[1] = db->src_bytes[2] = 0;
+    db->src_mtime_ns[0] = db->src_mtime_ns[1] = db->src_mtime_ns[2] = 0;
 }
 
 // ---- loading <base>.sz/.ky/.lb (or the same three arrays from host memory) ----------------------
 namespace {
+
+void file_stamp(const std::string& p, uint64_t& size, uint64_t& mtime_ns);
 
 // One staging set: a chunk of reference buckets with its keys and labels, host (pinned) and device.
 struct LoadStage {
@@ -864,6 +867,11 @@ int table_build_from_arrays(cuclark_db* db, const uint8_t* sz_in, const void* ky
     db->src_bytes[0] = base_path ? H : 0;
     db->src_bytes[1] = base_path ? total * (uint64_t)kb : 0;
     db->src_bytes[2] = base_path ? total * 2 : 0;
+    for (int i = 0; i < 3; i++) db->src_mtime_ns[i] = 0;
+    if (base_path) {
+        const char* ext[3] = {".sz", ".ky", ".lb"};
+        for (int i = 0; i < 3; i++) { uint64_t sz_i; file_stamp(std::string(base_path) + ext[i], sz_i, db->src_mtime_ns[i]); }
+    }
     if (!base_path && total != n_entries_file) { set_error("bucket sizes sum to %llu entries but %llu were passed", (unsigned long long)total, (unsigned long long)n_entries_file); return CUCLARK_ERR_ARG; }
     const double ms_scan = since(t_begin);
     const auto t_build = std::chrono::steady_clock::now();
@@ -1011,7 +1019,8 @@ int table_build_synthetic(cuclark_db* db, uint32_t seed, uint32_t n_targets, uin
 namespace {
 
 constexpr char CACHE_MAGIC[8] = {'C', 'U', 'C', 'B', '2', 'T', 'B', 'L'};
-constexpr uint32_t CACHE_VERSION = 3;   // 2: LOCAL tables have two candidate lines per minimizer; 3: the second one within 32 KB of the first
+constexpr uint32_t CACHE_VERSION = 4;   // 2: LOCAL tables have two candidate lines per minimizer; 3: the second one within 32 KB of the first;
+                                        // 4: source files identified by size AND modification time, LOCAL block size in the header
 constexpr size_t CACHE_IO_BYTES = 64ull << 20;
 
 struct CacheHeader {                 // 192 bytes, little endian
@@ -1021,7 +1030,9 @@ struct CacheHeader {                 // 192 bytes, little endian
     uint64_t htsize, M, lo, n_local, n_ovf, n_entries, n_spilled, n_spill_buckets;
     uint64_t src_bytes[3];           // sizes of the .sz/.ky/.lb the table was built from (0: not from files)
     uint64_t checksum;               // wrapping sum of the payload's 64-bit words times their position parity
-    uint64_t pad[6];
+    uint64_t src_mtime_ns[3];        // modification times of those files: a database rebuilt in place keeps its sizes
+    uint64_t local_alt_block;        // LOCAL: lines per block of the second candidate line (compile-time geometry)
+    uint64_t pad[2];
 };
 static_assert(sizeof(CacheHeader) == 192, "cache header layout");
 
@@ -1050,63 +1061,70 @@ int device_checksum(cuclark_db* db, const uint4* table, uint64_t n_table, const 
     return CUCLARK_OK;
 }
 
-struct IoBuffers {
-    void* h[2] = {nullptr, nullptr};
-    cudaEvent_t ev[2] = {nullptr, nullptr};
-    cudaStream_t st = nullptr;
-    int init() {
-        for (int i = 0; i < 2; i++) {
-            CK(cudaMallocHost(&h[i], CACHE_IO_BYTES));
-            CK(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
-        }
-        CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-        return CUCLARK_OK;
-    }
-    ~IoBuffers() {
-        for (int i = 0; i < 2; i++) { if (h[i]) cudaFreeHost(h[i]); if (ev[i]) cudaEventDestroy(ev[i]); }
-        if (st) cudaStreamDestroy(st);
-    }
-};
+// Table <-> file through CACHE_IO_THREADS host threads, each with its own pinned buffer and stream: piece i of the
+// payload belongs to thread i mod T, which reads it (pread) and copies it up (or copies it down and writes it) while
+// the other threads do the same for their pieces. One thread moved 5 GB/s out of /dev/shm (r01_cache_bench.json);
+// the PCIe link takes ~55 GB/s, so the file side needs the parallelism.
+constexpr int CACHE_IO_THREADS = 12;
 
-// device -> file, the copy of piece i+1 overlapping the write of piece i
-int stream_out(IoBuffers& io, FILE* f, const void* d_src, uint64_t bytes, const char* path) {
-    const uint8_t* src = static_cast<const uint8_t*>(d_src);
-    const uint64_t n_pieces = (bytes + CACHE_IO_BYTES - 1) / CACHE_IO_BYTES;
-    auto piece = [&](uint64_t i) { return std::min<uint64_t>(CACHE_IO_BYTES, bytes - i * CACHE_IO_BYTES); };
-    if (n_pieces) { CK(cudaMemcpyAsync(io.h[0], src, piece(0), cudaMemcpyDeviceToHost, io.st)); CK(cudaEventRecord(io.ev[0], io.st)); }
-    for (uint64_t i = 0; i < n_pieces; i++) {
-        if (i + 1 < n_pieces) {
-            CK(cudaMemcpyAsync(io.h[(i + 1) & 1], src + (i + 1) * CACHE_IO_BYTES, piece(i + 1), cudaMemcpyDeviceToHost, io.st));
-            CK(cudaEventRecord(io.ev[(i + 1) & 1], io.st));
-        }
-        CK(cudaEventSynchronize(io.ev[i & 1]));
-        if (fwrite(io.h[i & 1], 1, piece(i), f) != piece(i)) { set_error("write to %s failed", path); return CUCLARK_ERR_IO; }
+bool pwrite_all(int fd, const void* src, size_t n, uint64_t off) {
+    const uint8_t* p = static_cast<const uint8_t*>(src);
+    while (n) {
+        const ssize_t w = pwrite(fd, p, n, (off_t)off);
+        if (w <= 0) return false;
+        p += w; n -= (size_t)w; off += (uint64_t)w;
     }
+    return true;
+}
+
+// to_device: file[file_off ..) -> d_buf; else d_buf -> file[file_off ..)
+int stream_file(int device, int fd, uint64_t file_off, void* d_buf, uint64_t bytes, bool to_device, const char* path) {
+    const uint64_t n_pieces = (bytes + CACHE_IO_BYTES - 1) / CACHE_IO_BYTES;
+    if (!n_pieces) return CUCLARK_OK;
+    const int T = (int)std::min<uint64_t>(CACHE_IO_THREADS, n_pieces);
+    std::vector<int> rcs(T, CUCLARK_OK);
+    std::vector<std::string> errs(T);
+    parallel_for_threads(T, [&](int t) {
+        auto fail = [&](int rc, const std::string& m) { rcs[t] = rc; errs[t] = m; };
+        if (cudaSetDevice(device) != cudaSuccess) return fail(CUCLARK_ERR_CUDA, "cudaSetDevice failed");
+        void* h = nullptr;
+        cudaStream_t st = nullptr;
+        if (cudaMallocHost(&h, CACHE_IO_BYTES) != cudaSuccess || cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) {
+            cudaGetLastError();
+            if (h) cudaFreeHost(h);
+            return fail(CUCLARK_ERR_NOMEM, "pinned staging buffer for the table cache");
+        }
+        uint8_t* dev = static_cast<uint8_t*>(d_buf);
+        for (uint64_t i = (uint64_t)t; i < n_pieces && rcs[t] == CUCLARK_OK; i += (uint64_t)T) {
+            const uint64_t off = i * CACHE_IO_BYTES, n = std::min<uint64_t>(CACHE_IO_BYTES, bytes - off);
+            if (to_device) {
+                if (!pread_all(fd, h, n, file_off + off)) { fail(CUCLARK_ERR_IO, std::string(path) + " is truncated"); break; }
+                if (cudaMemcpyAsync(dev + off, h, n, cudaMemcpyHostToDevice, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess)
+                    fail(CUCLARK_ERR_CUDA, "H2D copy of the table cache failed");
+            } else {
+                if (cudaMemcpyAsync(h, dev + off, n, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) {
+                    fail(CUCLARK_ERR_CUDA, "D2H copy of the table failed");
+                    break;
+                }
+                if (!pwrite_all(fd, h, n, file_off + off)) fail(CUCLARK_ERR_IO, std::string("write to ") + path + " failed");
+            }
+        }
+        cudaGetLastError();
+        cudaStreamDestroy(st);
+        cudaFreeHost(h);
+    });
+    for (int t = 0; t < T; t++)
+        if (rcs[t] != CUCLARK_OK) { set_error("%s", errs[t].c_str()); return rcs[t]; }
     return CUCLARK_OK;
 }
 
-// file -> device, the read of piece i+1 overlapping the copy of piece i
-int stream_in(IoBuffers& io, FILE* f, void* d_dst, uint64_t bytes, const char* path) {
-    uint8_t* dst = static_cast<uint8_t*>(d_dst);
-    const uint64_t n_pieces = (bytes + CACHE_IO_BYTES - 1) / CACHE_IO_BYTES;
-    for (uint64_t i = 0; i < n_pieces; i++) {
-        const uint64_t n = std::min<uint64_t>(CACHE_IO_BYTES, bytes - i * CACHE_IO_BYTES);
-        if (i >= 2) CK(cudaEventSynchronize(io.ev[i & 1]));      // the copy that last used this buffer
-        if (fread(io.h[i & 1], 1, n, f) != n) { set_error("%s is truncated", path); return CUCLARK_ERR_IO; }
-        CK(cudaMemcpyAsync(dst + i * CACHE_IO_BYTES, io.h[i & 1], n, cudaMemcpyHostToDevice, io.st));
-        CK(cudaEventRecord(io.ev[i & 1], io.st));
-    }
-    CK(cudaStreamSynchronize(io.st));
-    return CUCLARK_OK;
-}
-
-uint64_t file_size_or_zero(const std::string& p) {
-    FILE* f = fopen(p.c_str(), "rb");
-    if (!f) return 0;
-    fseeko(f, 0, SEEK_END);
-    const uint64_t n = (uint64_t)ftello(f);
-    fclose(f);
-    return n;
+// size and modification time (ns) of a file; zeros if it cannot be stat'ed
+void file_stamp(const std::string& p, uint64_t& size, uint64_t& mtime_ns) {
+    struct stat sb;
+    size = mtime_ns = 0;
+    if (stat(p.c_str(), &sb) != 0) return;
+    size = (uint64_t)sb.st_size;
+    mtime_ns = (uint64_t)sb.st_mtim.tv_sec * 1000000000ull + (uint64_t)sb.st_mtim.tv_nsec;
 }
 
 }  // namespace
@@ -1121,30 +1139,29 @@ int table_save(cuclark_db* db, const char* path) {
     h.shard_index = db->cfg.shard_index; h.shard_count = db->cfg.shard_count; h.sfactor = db->src_sfactor;
     h.htsize = db->cfg.htsize; h.M = db->view.M; h.lo = db->view.lo; h.n_local = db->view.n_local; h.n_ovf = db->view.n_ovf;
     h.n_entries = db->n_entries; h.n_spilled = db->n_spilled; h.n_spill_buckets = db->n_spill_buckets;
-    for (int i = 0; i < 3; i++) h.src_bytes[i] = db->src_bytes[i];
+    for (int i = 0; i < 3; i++) { h.src_bytes[i] = db->src_bytes[i]; h.src_mtime_ns[i] = db->src_mtime_ns[i]; }
+    h.local_alt_block = LOCAL_ALT_BLOCK;
     CK(cudaDeviceSynchronize());
     int rc = device_checksum(db, db->d_table, h.n_local, db->d_ovf, h.n_ovf, &h.checksum);
     if (rc) return rc;
     const std::string tmp = std::string(path) + ".tmp";
-    FILE* f = fopen(tmp.c_str(), "wb");
-    if (!f) { set_error("Failed to open %s for writing", tmp.c_str()); return CUCLARK_ERR_IO; }
-    IoBuffers io;
-    rc = io.init();
-    if (rc == CUCLARK_OK && fwrite(&h, sizeof h, 1, f) != 1) { set_error("write to %s failed", tmp.c_str()); rc = CUCLARK_ERR_IO; }
-    if (rc == CUCLARK_OK) rc = stream_out(io, f, db->d_table, h.n_local * 32, tmp.c_str());
-    if (rc == CUCLARK_OK && h.n_ovf) rc = stream_out(io, f, db->d_ovf, h.n_ovf * 32, tmp.c_str());
-    if (fclose(f) != 0 && rc == CUCLARK_OK) { set_error("write to %s failed", tmp.c_str()); rc = CUCLARK_ERR_IO; }
+    const int fd = open(tmp.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    if (fd < 0) { set_error("Failed to open %s for writing", tmp.c_str()); return CUCLARK_ERR_IO; }
+    if (!pwrite_all(fd, &h, sizeof h, 0)) { set_error("write to %s failed", tmp.c_str()); rc = CUCLARK_ERR_IO; }
+    if (rc == CUCLARK_OK) rc = stream_file(db->cfg.device, fd, sizeof h, db->d_table, h.n_local * 32, false, tmp.c_str());
+    if (rc == CUCLARK_OK && h.n_ovf) rc = stream_file(db->cfg.device, fd, sizeof h + h.n_local * 32, db->d_ovf, h.n_ovf * 32, false, tmp.c_str());
+    if (close(fd) != 0 && rc == CUCLARK_OK) { set_error("write to %s failed", tmp.c_str()); rc = CUCLARK_ERR_IO; }
     if (rc == CUCLARK_OK && rename(tmp.c_str(), path) != 0) { set_error("cannot rename %s to %s", tmp.c_str(), path); rc = CUCLARK_ERR_IO; }
     if (rc != CUCLARK_OK) remove(tmp.c_str());
     return rc;
 }
 
 int table_load(cuclark_db* db, const char* path, const char* src_base, int sfactor) {
-    FILE* f = fopen(path, "rb");
-    if (!f) { set_error("Failed to open %s", path); return CUCLARK_ERR_IO; }
-    struct Closer { FILE* f; ~Closer() { fclose(f); } } closer{f};
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) { set_error("Failed to open %s", path); return CUCLARK_ERR_IO; }
+    struct Closer { int fd; ~Closer() { close(fd); } } closer{fd};
     CacheHeader h;
-    if (fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, CACHE_MAGIC, 8) != 0 || h.header_bytes != sizeof h) {
+    if (!pread_all(fd, &h, sizeof h, 0) || memcmp(h.magic, CACHE_MAGIC, 8) != 0 || h.header_bytes != sizeof h) {
         set_error("%s is not a cuclark_b200 table cache", path); return CUCLARK_ERR_FORMAT;
     }
     if (h.version != CACHE_VERSION) { set_error("%s: cache version %u, this library reads %u", path, h.version, CACHE_VERSION); return CUCLARK_ERR_FORMAT; }
@@ -1156,30 +1173,35 @@ int table_load(cuclark_db* db, const char* path, const char* src_base, int sfact
                   (unsigned long long)h.htsize, h.n_targets, h.shard_index, h.shard_count, h.sfactor, h.layout);
         return CUCLARK_ERR_FORMAT;
     }
+    // geometry: everything the kernels index with comes from here, so it is checked before anything is allocated
+    // (n_local < 2^32 and n_ovf < 2^40 also keep the byte counts below far from wrapping)
     if ((h.layout != LAYOUT_NARROW && h.layout != LAYOUT_WIDE && h.layout != LAYOUT_LOCAL) || h.M == 0 || h.n_local == 0 || h.n_local >= 0xFFFFFFFFull ||
-        h.lo + h.n_local > h.M || (h.layout == LAYOUT_NARROW && (h.k >= 32 || pow4((int)h.k) / h.M >= 0xFFFFFFFFull)) ||
-        (h.layout == LAYOUT_LOCAL && ((h.M & 3) || (h.lo & 3) || (h.n_local & 3) || (int)h.k < LOCAL_MIN_K || h.M / 4 < local_min_lines((int)h.k)))) {
+        h.n_ovf >= (1ull << 40) || h.lo > h.M || h.n_local > h.M - h.lo ||
+        (h.layout == LAYOUT_NARROW && (h.k >= 32 || pow4((int)h.k) / h.M >= 0xFFFFFFFFull)) ||
+        (h.layout == LAYOUT_LOCAL && ((h.M & 3) || (h.lo & 3) || (h.n_local & 3) || (int)h.k < LOCAL_MIN_K || h.M / 4 < local_min_lines((int)h.k) ||
+                                      h.local_alt_block != LOCAL_ALT_BLOCK))) {
         set_error("%s: inconsistent geometry", path); return CUCLARK_ERR_FORMAT;
     }
     if (src_base) {
+        // the cache belongs to the files it was built from: same sizes AND same modification times (a database
+        // rebuilt in place with as many k-mers keeps its sizes)
         const std::string b(src_base);
         const char* ext[3] = {".sz", ".ky", ".lb"};
         for (int i = 0; i < 3; i++) {
-            if (file_size_or_zero(b + ext[i]) != h.src_bytes[i]) {
-                set_error("%s does not belong to %s%s (size differs)", path, src_base, ext[i]); return CUCLARK_ERR_FORMAT;
+            uint64_t sz_i, mt_i;
+            file_stamp(b + ext[i], sz_i, mt_i);
+            if (sz_i != h.src_bytes[i] || mt_i != h.src_mtime_ns[i]) {
+                set_error("%s does not belong to %s%s (size or modification time differs)", path, src_base, ext[i]); return CUCLARK_ERR_FORMAT;
             }
         }
     }
-    fseeko(f, 0, SEEK_END);
-    if ((uint64_t)ftello(f) != sizeof h + (h.n_local + h.n_ovf) * 32) { set_error("%s is truncated", path); return CUCLARK_ERR_FORMAT; }
-    fseeko(f, sizeof h, SEEK_SET);
+    struct stat sb;
+    if (fstat(fd, &sb) != 0 || (uint64_t)sb.st_size != sizeof h + (h.n_local + h.n_ovf) * 32) { set_error("%s is truncated", path); return CUCLARK_ERR_FORMAT; }
     uint4 *table = nullptr, *ovf = nullptr;
     if (cudaMalloc(&table, h.n_local * 32) != cudaSuccess) { cudaGetLastError(); set_error("cudaMalloc of %.2f GB table failed", h.n_local * 32 / 1e9); return CUCLARK_ERR_NOMEM; }
     if (h.n_ovf && cudaMalloc(&ovf, h.n_ovf * 32) != cudaSuccess) { cudaGetLastError(); cudaFree(table); set_error("cudaMalloc of overflow table failed"); return CUCLARK_ERR_NOMEM; }
-    IoBuffers io;
-    int rc = io.init();
-    if (rc == CUCLARK_OK) rc = stream_in(io, f, table, h.n_local * 32, path);
-    if (rc == CUCLARK_OK && h.n_ovf) rc = stream_in(io, f, ovf, h.n_ovf * 32, path);
+    int rc = stream_file(db->cfg.device, fd, sizeof h, table, h.n_local * 32, true, path);
+    if (rc == CUCLARK_OK && h.n_ovf) rc = stream_file(db->cfg.device, fd, sizeof h + h.n_local * 32, ovf, h.n_ovf * 32, true, path);
     uint64_t sum = 0;
     if (rc == CUCLARK_OK) rc = device_checksum(db, table, h.n_local, ovf, h.n_ovf, &sum);
     if (rc == CUCLARK_OK && sum != h.checksum) { set_error("%s: checksum mismatch (file is corrupt)", path); rc = CUCLARK_ERR_FORMAT; }
@@ -1193,7 +1215,7 @@ int table_load(cuclark_db* db, const char* path, const char* src_base, int sfact
     if (h.layout == LAYOUT_LOCAL) { db->view.NL = h.M / 4; db->view.magicNL = (uint64_t)((((__uint128_t)1) << 64) / db->view.NL); set_local_divmod(db->view); db->view.line_lo = (uint32_t)(h.lo >> 2); db->view.line_n = (uint32_t)(h.n_local >> 2); }
     db->n_entries = h.n_entries; db->n_spilled = h.n_spilled; db->n_spill_buckets = h.n_spill_buckets;
     db->src_sfactor = (int)h.sfactor;
-    for (int i = 0; i < 3; i++) db->src_bytes[i] = h.src_bytes[i];
+    for (int i = 0; i < 3; i++) { db->src_bytes[i] = h.src_bytes[i]; db->src_mtime_ns[i] = h.src_mtime_ns[i]; }
     return CUCLARK_OK;
 }
 

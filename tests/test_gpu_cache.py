@@ -68,8 +68,16 @@ def test_cache_refuses_corrupt_foreign_and_stale_files(light_small, tmp_path):
         # not a cache at all
         open(path, "wb").write(b"Object_ID,Length\n" * 100)
         assert not g.load_table(path)
-        # stale: the source files changed size
+        # stale: a database rebuilt in place with as many k-mers keeps its sizes; the modification time gives it away
         open(path, "wb").write(blob)
+        assert g.load_table(path, src_base=base)
+        import os
+        st_ky = os.stat(base + ".ky")
+        os.utime(base + ".ky", ns=(st_ky.st_atime_ns, st_ky.st_mtime_ns + 2_000_000_000))
+        assert not g.load_table(path, src_base=base)
+        os.utime(base + ".ky", ns=(st_ky.st_atime_ns, st_ky.st_mtime_ns))
+        assert g.load_table(path, src_base=base)
+        # stale: the source files changed size
         with open(base + ".lb", "ab") as f:
             f.write(b"\0\0")
         assert not g.load_table(path, src_base=base)
