@@ -168,13 +168,22 @@ def measured_peaks():
 
 
 def ncu_traffic(workload_key: str, lookups: int):
-    """DRAM bytes per classify launch: bytes/lookup from the committed `ncu --set full` capture
-    (profiles/traffic.json) x the lookups of one launch. None if no capture is committed."""
+    """DRAM bytes per classify launch: bytes/lookup from the committed `ncu --set full` capture (profiles/traffic.json,
+    written by tools/refresh_traffic.py) x the lookups of one launch. The capture names the SHA-1 of the kernel sources
+    it was taken from: if the sources differ (the kernel changed since) or no capture exists the figure is None, with
+    the reason beside it."""
+    import hashlib
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            return json.load(f)[workload_key]["dram_bytes_per_lookup"] * lookups
-    except Exception:
-        return None
+            e = json.load(f)[workload_key]
+        h = hashlib.sha1()
+        for src in ("classify.cu", "common.cuh", "hits.cuh", "kmerwin.cuh"):
+            h.update(open(os.path.join(ROOT, "cuclark_b200", "csrc", src), "rb").read())
+        if e.get("kernel_source_sha1") != h.hexdigest():
+            return None, "stale: the kernel sources changed since the ncu capture (tools/refresh_traffic.py)"
+        return e["dram_bytes_per_lookup"] * lookups, f"ncu --set full, {e.get('report')}, {e['dram_bytes_per_lookup']:.1f} B per lookup"
+    except Exception as ex:
+        return None, f"no capture: {ex!r}"
 
 
 # ---------------------------------------------------------------- CPU legs (oracle: checker/baseline only)
@@ -637,6 +646,7 @@ def run_b200(args):
     if rank == 0:
         peak, peak_src = measured_peaks()
         kernel_ms = float(np.mean(step_ms))
+        traffic, traffic_src = ncu_traffic("config2" if st["layout"] == 1 else "config2_layout%d" % st["layout"], lookups)
         achieved = lookups * BYTES_PER_LOOKUP / (kernel_ms * 1e-3) / 1e9
         value = lookups_all * args.steps / (total_ms_max * 1e-3)
         line = {
@@ -649,7 +659,7 @@ def run_b200(args):
                       "layout": {1: "narrow", 2: "wide", 3: "local"}.get(st["layout"], str(st["layout"])), "overflow_entries": st["n_spilled"],
                       "overflowed_buckets": st["n_spill_buckets"], "build_s": build_s},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic("config2" if st["layout"] == 1 else "config2_layout%d" % st["layout"], lookups), "algorithmic_bytes": lookups * BYTES_PER_LOOKUP, "peak_source": peak_src,
+                         "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes": lookups * BYTES_PER_LOOKUP, "peak_source": peak_src,
                          "kernel": "k_classify<%s,false>" % {1: "NARROW", 2: "WIDE", 3: "LOCAL"}.get(st["layout"], "?"), "kernel_ms": kernel_ms,
                          "bytes_per_lookup": BYTES_PER_LOOKUP, "lookups_per_launch": lookups,
                          "random_access_peak": random_gbs, "frac_random_access": achieved / random_gbs,

@@ -22,6 +22,7 @@
 // Because a canonical k-mer has exactly one home shard the labels, and so every count, equal the single-table
 // result bit for bit. Hashed table layouts only (NARROW / WIDE); the single-device LOCAL layout does not shard
 // at bacterial scale (its line count is bound to 2^30).
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -213,48 +214,156 @@ struct ProbeParams {
     RouteHeader* my_hdr;
 };
 
+// One block of 256 k-mers: probe them in this shard's table, store the labels into the asker's label array.
 template <int LAYOUT>
-__global__ void __launch_bounds__(256, 3) k_route_probe(const ProbeParams p) {
+__device__ __forceinline__ void probe_block(const ProbeParams& p, const uint64_t (&c)[BLK / 32], uint16_t* dst, int lane,
+                                            unsigned long long& probed) {
+    const TableView& T = p.t;
+#pragma unroll
+    for (int h = 0; h < (int)(BLK / 32); h += 4) {
+        Sector sec[4];
+        uint64_t q[4], b[4];
+        bool live[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            divmod_M(c[h + j], T.M, T.magic, q[j], b[j]);
+            b[j] -= T.lo;
+            live[j] = c[h + j] != SENTINEL && b[j] < T.n_local;
+            if (live[j]) sec[j] = load_sector(T.buckets + 2 * b[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            uint32_t label = NO_LABEL;
+            if (live[j]) {
+                label = match_sector<LAYOUT>(sec[j], q[j]);
+                if (label == NO_LABEL && sector_overflowed(sec[j])) label = ovf_lookup(T, c[h + j]);
+                if (label >= p.n_targets) label = NO_LABEL;
+                probed++;
+            }
+            dst[32 * (h + j) + lane] = label == NO_LABEL ? LABEL_NONE : (uint16_t)label;      // 64-byte stores, posted
+        }
+    }
+}
+
+// Every warp walks its share of the block list addressed to this shard in rank g's region. The k-mers of the NEXT
+// block (and the list entry after it) are already on their way over NVLink while the current block is probed:
+// a remote load takes microseconds, and without the prefetch the probe rate fell from 33 G/s (2 GPUs, half of the
+// blocks remote) to 22 G/s (8 GPUs, 7/8 remote).
+template <int LAYOUT>
+__global__ void __launch_bounds__(256, 2) k_route_probe(const ProbeParams p) {
     const int lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
-    const TableView& T = p.t;
     unsigned long long probed = 0;
     for (int gi = 0; gi < p.n_ranks; gi++) {
         const int g = (p.rank + gi) % p.n_ranks;              // start with the own region, then round the ring
         const RegionView R = region_view(p.region[g], p.n_ranks, p.cap_blocks);
         const uint32_t nb = min(__ldcv(&R.hdr->nblk[p.rank]), p.cap_blocks);
         const uint32_t* list = R.blocklist + (size_t)p.rank * p.cap_blocks;
-        for (uint32_t i = warp; i < nb; i += n_warps) {
-            const uint32_t blk = __ldcv(&list[i]);
-            const uint64_t* src = R.arena + (size_t)blk * BLK;
-            uint16_t* dst = R.labels + (size_t)blk * BLK;
-            uint64_t c[BLK / 32];
+        uint32_t i = warp;
+        if (i >= nb) continue;
+        uint32_t blk = __ldcv(&list[i]);
+        uint32_t blk_next = i + n_warps < nb ? __ldcv(&list[i + n_warps]) : 0;
+        uint64_t c[BLK / 32];
 #pragma unroll
-            for (int j = 0; j < (int)(BLK / 32); j++) c[j] = __ldcv(&src[32 * j + lane]);     // 256-byte requests over NVLink
+        for (int j = 0; j < (int)(BLK / 32); j++) c[j] = __ldcv(&R.arena[(size_t)blk * BLK + 32 * j + lane]);     // 256-byte requests
+        for (;;) {
+            const uint32_t i_next = i + n_warps;
+            const bool more = i_next < nb;
+            uint64_t cn[BLK / 32];
+            uint32_t blk_next2 = 0;
+            if (more) {
 #pragma unroll
-            for (int h = 0; h < (int)(BLK / 32); h += 4) {
-                Sector sec[4];
-                uint64_t q[4], b[4];
-                bool live[4];
+                for (int j = 0; j < (int)(BLK / 32); j++) cn[j] = __ldcv(&R.arena[(size_t)blk_next * BLK + 32 * j + lane]);
+                if (i_next + n_warps < nb) blk_next2 = __ldcv(&list[i_next + n_warps]);
+            }
+            probe_block<LAYOUT>(p, c, R.labels + (size_t)blk * BLK, lane, probed);
+            if (!more) break;
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    divmod_M(c[h + j], T.M, T.magic, q[j], b[j]);
-                    b[j] -= T.lo;
-                    live[j] = c[h + j] != SENTINEL && b[j] < T.n_local;
-                    if (live[j]) sec[j] = load_sector(T.buckets + 2 * b[j]);
+            for (int j = 0; j < (int)(BLK / 32); j++) c[j] = cn[j];
+            blk = blk_next; blk_next = blk_next2; i = i_next;
+        }
+    }
+    for (int o = 16; o; o >>= 1) probed += __shfl_xor_sync(0xFFFFFFFFu, probed, o);
+    if (lane == 0 && probed) atomicAdd(&p.my_hdr->probed, probed);
+}
+
+// ---- the same walk with the k-mer blocks brought in by the TMA (bulk async copies into shared memory) ------
+// Each warp owns a ring of PROBE_STAGES 2 KB stages and one mbarrier per stage; lane 0 arms the barrier with the
+// byte count and issues `cp.async.bulk` from the (peer) arena, the warp waits on the barrier's phase before it
+// reads the stage. Up to PROBE_STAGES blocks per warp are in flight over NVLink while one is being probed, without
+// holding them in registers. A warp takes a CONTIGUOUS range of the block list so that 32 list entries arrive
+// with one coalesced load.
+constexpr int PROBE_STAGES = 4;
+constexpr int PROBE_WARPS = 8;
+struct alignas(128) ProbeWarpSmem {
+    uint64_t kmers[PROBE_STAGES][BLK];
+    uint64_t bar[PROBE_STAGES];
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    }
+}
+
+template <int LAYOUT>
+__global__ void __launch_bounds__(PROBE_WARPS * 32, 2) k_route_probe_tma(const ProbeParams p) {
+    extern __shared__ __align__(128) uint8_t probe_smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    ProbeWarpSmem& S = reinterpret_cast<ProbeWarpSmem*>(probe_smem)[wib];
+    if (lane == 0)
+        for (int s = 0; s < PROBE_STAGES; s++) mbar_init(&S.bar[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    const uint32_t warp = blockIdx.x * PROBE_WARPS + wib, n_warps = gridDim.x * PROBE_WARPS;
+    unsigned long long probed = 0;
+    uint32_t n_issued = 0, n_used = 0;           // blocks this warp has requested / consumed so far (stage = n % STAGES)
+    for (int gi = 0; gi < p.n_ranks; gi++) {
+        const int g = (p.rank + gi) % p.n_ranks;
+        const RegionView R = region_view(p.region[g], p.n_ranks, p.cap_blocks);
+        const uint32_t nb = min(__ldcv(&R.hdr->nblk[p.rank]), p.cap_blocks);
+        const uint32_t* list = R.blocklist + (size_t)p.rank * p.cap_blocks;
+        const uint32_t lo = (uint32_t)((uint64_t)nb * warp / n_warps), hi = (uint32_t)((uint64_t)nb * (warp + 1) / n_warps);
+        uint32_t entry_next = lo + lane < hi ? __ldcv(&list[lo + lane]) : 0;
+        for (uint32_t base = lo; base < hi; base += 32) {
+            const uint32_t entry = entry_next;                                   // block ids of this group of <= 32 blocks
+            const uint32_t m = min(32u, hi - base);
+            entry_next = base + 32 + lane < hi ? __ldcv(&list[base + 32 + lane]) : 0;
+            auto issue = [&](uint32_t t) {                                       // warp-uniform t
+                const uint32_t blk = __shfl_sync(0xFFFFFFFFu, entry, t);
+                const uint32_t st = n_issued % PROBE_STAGES;
+                if (lane == 0) {
+                    mbar_expect_tx(&S.bar[st], BLK * 8);
+                    bulk_g2s(S.kmers[st], R.arena + (size_t)blk * BLK, BLK * 8, &S.bar[st]);
                 }
+                n_issued++;
+            };
+            for (uint32_t t = 0; t < min((uint32_t)PROBE_STAGES, m); t++) issue(t);
+            for (uint32_t t = 0; t < m; t++) {
+                const uint32_t st = n_used % PROBE_STAGES, parity = (n_used / PROBE_STAGES) & 1u;
+                mbar_wait(&S.bar[st], parity);
+                uint64_t c[BLK / 32];
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    uint32_t label = NO_LABEL;
-                    if (live[j]) {
-                        label = match_sector<LAYOUT>(sec[j], q[j]);
-                        if (label == NO_LABEL && sector_overflowed(sec[j])) label = ovf_lookup(T, c[h + j]);
-                        if (label >= p.n_targets) label = NO_LABEL;
-                        probed++;
-                    }
-                    dst[32 * (h + j) + lane] = label == NO_LABEL ? LABEL_NONE : (uint16_t)label;
-                }
+                for (int j = 0; j < (int)(BLK / 32); j++) c[j] = S.kmers[st][32 * j + lane];
+                n_used++;
+                __syncwarp();                                                    // the stage is free again
+                if (t + PROBE_STAGES < m) issue(t + PROBE_STAGES);
+                const uint32_t blk = __shfl_sync(0xFFFFFFFFu, entry, t);
+                probe_block<LAYOUT>(p, c, R.labels + (size_t)blk * BLK, lane, probed);
             }
         }
     }
@@ -504,9 +613,21 @@ int route_probe(cuclark_db* db, cudaStream_t st) {
     p.n_targets = (uint32_t)db->cfg.n_targets;
     for (int i = 0; i < ROUTE_MAX_RANKS; i++) p.region[i] = i < r->n_ranks ? r->peer[i] : nullptr;
     p.my_hdr = reinterpret_cast<RouteHeader*>(r->region);
-    const int blocks = r->sm_count * 3;
-    if (db->view.layout == LAYOUT_NARROW) k_route_probe<LAYOUT_NARROW><<<blocks, 256, 0, st>>>(p);
-    else k_route_probe<LAYOUT_WIDE><<<blocks, 256, 0, st>>>(p);
+    const int blocks = r->sm_count * 2;
+    static const bool use_ldg = getenv("CUCLARK_ROUTE_LDG") != nullptr;       // the register-prefetch variant, for A/B runs
+    if (use_ldg) {
+        if (db->view.layout == LAYOUT_NARROW) k_route_probe<LAYOUT_NARROW><<<blocks, 256, 0, st>>>(p);
+        else k_route_probe<LAYOUT_WIDE><<<blocks, 256, 0, st>>>(p);
+    } else {
+        const size_t smem = sizeof(ProbeWarpSmem) * PROBE_WARPS;
+        if (db->view.layout == LAYOUT_NARROW) {
+            CK(cudaFuncSetAttribute(k_route_probe_tma<LAYOUT_NARROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_route_probe_tma<LAYOUT_NARROW><<<blocks, PROBE_WARPS * 32, smem, st>>>(p);
+        } else {
+            CK(cudaFuncSetAttribute(k_route_probe_tma<LAYOUT_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_route_probe_tma<LAYOUT_WIDE><<<blocks, PROBE_WARPS * 32, smem, st>>>(p);
+        }
+    }
     CK(cudaGetLastError());
     count_launches(1);
     return CUCLARK_OK;
