@@ -38,7 +38,7 @@ ABI_SYMBOLS = [
     "cuclark_build_database", "cuclark_save_table", "cuclark_load_table", "cuclark_plan_table",
     "cuclark_route_alloc", "cuclark_route_free", "cuclark_route_export", "cuclark_route_import", "cuclark_route_connect",
     "cuclark_route_scatter", "cuclark_route_probe", "cuclark_route_gather", "cuclark_route_get_stats",
-    "cuclark_classify_routed_device", "cuclark_clone_table", "cuclark_device_info",
+    "cuclark_classify_routed_device", "cuclark_clone_table", "cuclark_device_info", "cuclark_synth_fastq_pair_device",
 ]
 
 
@@ -157,6 +157,7 @@ def load_library():
             if fn is not None and name != "cuclark_last_error":
                 fn.restype = ci
         return lib
+    lib.cuclark_synth_fastq_pair_device.argtypes = [vp, u32, u32, u32, u64, u64, sz, ci, ci, ci, ci, vp, vp]
     lib.cuclark_clone_table.argtypes = [vp, vp]
     lib.cuclark_device_info.argtypes = [ci, P(ci), P(u64), P(u64)]
     lib.cuclark_route_alloc.argtypes = [vp, ci, sz]
@@ -435,6 +436,12 @@ class CuClarkDB:
         self._check(self._lib.cuclark_synth_fastq_device(self._h, seed, genome_seed, n_targets, genome_len, first_read,
                                                           n_reads, read_len, pct_random, sub_per_10k, d_text,
                                                           stream or None))
+
+    def synth_fastq_pair_device(self, seed, genome_seed, n_targets, genome_len, first_read, n_reads, read_len,
+                                pct_random, sub_per_10k, mate: int, d_text: int, stream: int = 0):
+        self._check(self._lib.cuclark_synth_fastq_pair_device(self._h, seed, genome_seed, n_targets, genome_len, first_read,
+                                                               n_reads, read_len, pct_random, sub_per_10k, mate, d_text,
+                                                               stream or None))
 
     def gather_bench(self, n_probes: int, bytes_per_probe: int = 32, ilp: int = 4, iters: int = 5) -> float:
         ms = C.c_double()

@@ -423,6 +423,16 @@ int cuclark_synth_fastq_device(cuclark_db* db, uint32_t seed, uint32_t genome_se
                               sub_per_10k, d_text, stream ? (cudaStream_t)stream : db->stream);
 }
 
+int cuclark_synth_fastq_pair_device(cuclark_db* db, uint32_t seed, uint32_t genome_seed, uint32_t n_targets,
+                                    uint64_t genome_len, uint64_t first_read, size_t n_reads, int read_len,
+                                    int pct_random, int sub_per_10k, int mate, uint8_t* d_text, void* stream) {
+    if (!db || !d_text || (mate != 1 && mate != 2)) { set_error("bad argument"); return CUCLARK_ERR_ARG; }
+    int rc = use_device(db);
+    if (rc) return rc;
+    return synth_fastq_launch(seed, genome_seed, n_targets, genome_len, first_read, n_reads, read_len, pct_random,
+                              sub_per_10k, d_text, stream ? (cudaStream_t)stream : db->stream, mate);
+}
+
 int cuclark_gather_bench(cuclark_db* db, uint64_t n_probes, int bytes_per_probe, int ilp, int iters, double* ms_out) {
     if (!db || !ms_out || iters < 1) { set_error("bad argument"); return CUCLARK_ERR_ARG; }
     int rc = use_device(db);

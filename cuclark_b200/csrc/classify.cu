@@ -411,9 +411,11 @@ __global__ void k_synth_reads(uint32_t seed, uint32_t genome_seed, uint32_t n_ta
 
 // Same reads as k_synth_reads, as 4-line FASTQ text with fixed-width records:
 // "@r%09llu\n" + bases + "\n+\n" + 'I' * read_len + "\n"  (16 + 2*read_len bytes each).
+// mate = 0: the single-end read; 1 / 2: the mates of a pair (BASELINE configs[2]): mate 1 is that same read, mate 2 lies
+// 2 x read_len further along the same target (clamped to its end) on the OPPOSITE strand, with its own substitutions.
 __global__ void k_synth_fastq(uint32_t seed, uint32_t genome_seed, uint32_t n_targets, uint64_t genome_len,
                               uint64_t first_read, uint32_t n_reads, int read_len, int pct_random, int sub_per_10k,
-                              uint8_t* text) {
+                              uint8_t* text, int mate) {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_reads) return;
     const size_t rec = 16 + 2 * (size_t)read_len;
@@ -422,8 +424,10 @@ __global__ void k_synth_fastq(uint32_t seed, uint32_t genome_seed, uint32_t n_ta
     const uint64_t h1 = synth::key(synth::TAG_READ, seed, i, 0), h2 = synth::key(synth::TAG_READ, seed, i, 1);
     const bool is_random = (h1 % 100) < (uint64_t)pct_random;
     const uint32_t target = (uint32_t)((h1 >> 8) % n_targets);
-    const bool is_rc = (h1 >> 40) & 1;
-    const uint64_t pos = h2 % (genome_len - read_len + 1);
+    bool is_rc = (h1 >> 40) & 1;
+    uint64_t pos = h2 % (genome_len - read_len + 1);
+    const uint64_t jo = mate == 2 ? 1024 : 0;            // mate 2 draws its random bases / substitutions from other counters
+    if (mate == 2) { pos = min(pos + 2 * (uint64_t)read_len, genome_len - read_len); is_rc = !is_rc; }
     o[0] = '@'; o[1] = 'r';
     uint64_t v = i % 1000000000ull;
     for (int d = 8; d >= 0; d--) { o[2 + d] = (uint8_t)('0' + v % 10); v /= 10; }
@@ -431,11 +435,11 @@ __global__ void k_synth_fastq(uint32_t seed, uint32_t genome_seed, uint32_t n_ta
     uint8_t* sq = o + 12;
     for (int j = 0; j < read_len; j++) {
         uint32_t code;
-        if (is_random) code = (uint32_t)(synth::key(synth::TAG_RBASE, seed, i, (uint64_t)(j >> 5)) >> (2 * (j & 31))) & 3u;
+        if (is_random) code = (uint32_t)(synth::key(synth::TAG_RBASE, seed, i, jo + (uint64_t)(j >> 5)) >> (2 * (j & 31))) & 3u;
         else if (is_rc) code = 3u - synth::genome_base(genome_seed, target, pos + (read_len - 1 - j));
         else code = synth::genome_base(genome_seed, target, pos + j);
         if (sub_per_10k) {
-            const uint64_t sh = synth::key(synth::TAG_SUB, seed, i, (uint64_t)j);
+            const uint64_t sh = synth::key(synth::TAG_SUB, seed, i, jo + (uint64_t)j);
             if ((sh % 10000) < (uint64_t)sub_per_10k) code = (code + 1 + (uint32_t)((sh >> 20) % 3)) & 3u;
         }
         sq[j] = (uint8_t)"ACGT"[code];
@@ -569,12 +573,13 @@ int synth_reads_launch(uint32_t seed, uint32_t genome_seed, uint32_t n_targets, 
 }
 
 int synth_fastq_launch(uint32_t seed, uint32_t genome_seed, uint32_t n_targets, uint64_t genome_len, uint64_t first_read,
-                       size_t n_reads, int read_len, int pct_random, int sub_per_10k, uint8_t* d_text, cudaStream_t st) {
+                       size_t n_reads, int read_len, int pct_random, int sub_per_10k, uint8_t* d_text, cudaStream_t st, int mate) {
+    if (mate < 0 || mate > 2 || (mate && genome_len < 3ull * (uint64_t)read_len)) { set_error("bad mate / genome too short for pairs"); return CUCLARK_ERR_ARG; }
     if (read_len < 1 || read_len > 65535 || genome_len < (uint64_t)read_len) { set_error("bad read_len"); return CUCLARK_ERR_ARG; }
     if (n_reads > 0xFFFFFFF0ull) { set_error("too many reads"); return CUCLARK_ERR_ARG; }
     if (n_reads)
         k_synth_fastq<<<(unsigned)((n_reads + 255) / 256), 256, 0, st>>>(seed, genome_seed, n_targets, genome_len, first_read,
-                                                                         (uint32_t)n_reads, read_len, pct_random, sub_per_10k, d_text);
+                                                                         (uint32_t)n_reads, read_len, pct_random, sub_per_10k, d_text, mate);
     CK(cudaGetLastError());
     return CUCLARK_OK;
 }

@@ -16,11 +16,15 @@
 //    GPUs exchange k-mers and labels (csrc/route.cu);
 //  * a missing database is built on the GPU (cuclark_build_database) from FASTA targets, byte-identical
 //    to the reference's files; --tsk, spectrum/FASTQ targets and the 3rd targets column are not supported.
+#include <fcntl.h>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
 #include <sys/time.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <iostream>
@@ -305,7 +309,18 @@ static void load_database(Cli& c) {
 }
 
 // src/CuCLARK_hh.hh:512-573
-static void run_simple(Cli& c, const char* objects, const char* result, bool paired) {
+static int csv_file_sink(void* user, const char* data, size_t n, uint64_t offset) {
+    const int fd = (int)(intptr_t)user;
+    while (n) {
+        const ssize_t w = pwrite(fd, data, n, (off_t)offset);
+        if (w <= 0) return -1;
+        data += w; n -= (size_t)w; offset += (uint64_t)w;
+    }
+    return 0;
+}
+
+// `memory`: the reads are already in memory (joined mates) instead of in the file `objects`
+static void run_simple(Cli& c, const char* objects, const char* result, bool paired, const vector<char>* memory = nullptr) {
     const string csv = string(result) + ".csv";
     vector<const char*> name_ptrs;
     for (size_t t = 1; t < c.names.size(); t++) name_ptrs.push_back(c.names[t].c_str());
@@ -320,7 +335,17 @@ static void run_simple(Cli& c, const char* objects, const char* result, bool pai
     struct timeval t0, t1;
     gettimeofday(&t0, nullptr);
     cerr << (c.ext ? "Writing extended results... " : "Writing results... ") << endl;
-    const int rc = cuclark_classify_file_multi(c.dbs.data(), (int)c.dbs.size(), objects, csv.c_str(), &o, &st);
+    int rc;
+    if (memory) {
+        const int ofd = open(csv.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+        if (ofd < 0) { cerr << "Failed to create/open file result: " << csv << endl; return; }
+        rc = memory->empty() ? CUCLARK_ERR_FORMAT
+                             : cuclark_classify_text_multi(c.dbs.data(), (int)c.dbs.size(), (const uint8_t*)memory->data(), memory->size(), &o,
+                                                           csv_file_sink, (void*)(intptr_t)ofd, &st);
+        close(ofd);
+    } else {
+        rc = cuclark_classify_file_multi(c.dbs.data(), (int)c.dbs.size(), objects, csv.c_str(), &o, &st);
+    }
     if (rc == CUCLARK_ERR_IO) { cerr << cuclark_last_error() << endl; return; }
     if (rc == CUCLARK_ERR_FORMAT) { cerr << cuclark_last_error() << endl; exit(-1); }
     if (rc) die_lib("cuclark_classify_file");
@@ -333,34 +358,74 @@ static void run_simple(Cli& c, const char* objects, const char* result, bool pai
     cout << " - Results stored in " << csv << endl;
 }
 
-// src/file.cc:205-268: FASTQ mates -> ">id\n<seq1>N<seq2>\n"; ids = first token split on ' ', '/', '\t', '@'
-static void merge_paired_files(const char* f1, const char* f2, const char* out) {
-    FILE* a = fopen(f1, "r");
-    FILE* b = fopen(f2, "r");
-    string l1, l2;
-    get_line(a, l1);
-    get_line(b, l2);
-    if (l1.empty() || l2.empty() || l1[0] != l2[0]) { perror("Error: the files have different format!"); exit(1); }
-    if (l1[0] != '@') { perror("Error: paired-end reads must be FASTQ files!"); exit(1); }
-    rewind(a);
-    rewind(b);
-    FILE* o = fopen(out, "wb");
-    if (!o) { cerr << "Failed to create " << out << endl; exit(1); }
-    vector<char> iobuf(8 << 20);
-    setvbuf(o, iobuf.data(), _IOFBF, iobuf.size());
-    while (get_line(a, l1) && get_line(b, l2)) {
-        if (l1.empty() || l2.empty() || l1[0] != '@' || l2[0] != '@') continue;
-        const vector<string> e1 = tokens(l1, " /\t@", 1), e2 = tokens(l2, " /\t@", 1);
-        const string id1 = e1.empty() ? "" : e1[0], id2 = e2.empty() ? "" : e2[0];
-        if (id1 != id2) { perror("Error: read id does not match between files!"); exit(1); }
-        if (!(get_line(a, l1) && get_line(b, l2))) { perror("Error: Found read without sequence"); exit(1); }
-        fputc('>', o); fwrite(id1.data(), 1, id1.size(), o); fputc('\n', o);
-        fwrite(l1.data(), 1, l1.size(), o); fputc('N', o); fwrite(l2.data(), 1, l2.size(), o); fputc('\n', o);
-        if (get_line(a, l1) && get_line(b, l2)) { if (get_line(a, l1) && get_line(b, l2)) continue; }
+// A whole file, mapped read-only.
+struct Mapped {
+    const char* p = nullptr;
+    size_t n = 0;
+    int fd = -1;
+    bool open_path(const char* path) {
+        fd = open(path, O_RDONLY);
+        struct stat sb;
+        if (fd < 0 || fstat(fd, &sb) != 0) return false;
+        n = (size_t)sb.st_size;
+        if (n == 0) return true;
+        void* m = mmap(nullptr, n, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (m == MAP_FAILED) return false;
+        madvise(m, n, MADV_SEQUENTIAL);
+        p = (const char*)m;
+        return true;
     }
-    fclose(a);
-    fclose(b);
-    fclose(o);
+    ~Mapped() {
+        if (p) munmap((void*)p, n);
+        if (fd >= 0) close(fd);
+    }
+};
+
+// src/file.cc:205-268: FASTQ mates -> ">id\n<seq1>N<seq2>\n"; ids = first token of the header split on ' ', '/',
+// '\t', '@'. The reference writes the joined reads to <file1>_ConcatenatedByCLARK.fa with getline/string code and
+// classifies that file; here the two files are walked with memchr and the joined reads stay in memory.
+static void merge_paired(const char* f1, const char* f2, vector<char>& out) {
+    Mapped a, b;
+    if (!a.open_path(f1) || !b.open_path(f2) || a.n == 0 || b.n == 0 || a.p[0] != b.p[0]) { perror("Error: the files have different format!"); exit(1); }
+    if (a.p[0] != '@') { perror("Error: paired-end reads must be FASTQ files!"); exit(1); }
+    out.clear();
+    out.reserve(a.n / 2 + b.n / 2 + (1 << 20));
+    size_t ia = 0, ib = 0;
+    // [s, e) of the line at i (without the newline), i moved past it; false at end of file
+    auto line = [](const Mapped& m, size_t& i, size_t& s, size_t& e) {
+        if (i >= m.n) return false;
+        const char* nl = (const char*)memchr(m.p + i, '\n', m.n - i);
+        s = i;
+        e = nl ? (size_t)(nl - m.p) : m.n;
+        i = nl ? e + 1 : m.n;
+        return true;
+    };
+    auto first_token = [](const char* p, size_t s, size_t e, size_t& ts, size_t& te) {
+        auto sep = [](char c) { return c == ' ' || c == '/' || c == '\t' || c == '@'; };
+        while (s < e && sep(p[s])) s++;
+        ts = s;
+        while (s < e && !sep(p[s])) s++;
+        te = s;
+    };
+    size_t s1, e1, s2, e2;
+    while (line(a, ia, s1, e1) && line(b, ib, s2, e2)) {
+        if (e1 == s1 || e2 == s2 || a.p[s1] != '@' || b.p[s2] != '@') continue;
+        size_t t1s, t1e, t2s, t2e;
+        first_token(a.p, s1, e1, t1s, t1e);
+        first_token(b.p, s2, e2, t2s, t2e);
+        if (t1e - t1s != t2e - t2s || memcmp(a.p + t1s, b.p + t2s, t1e - t1s) != 0) { perror("Error: read id does not match between files!"); exit(1); }
+        size_t q1s, q1e, q2s, q2e;
+        if (!(line(a, ia, q1s, q1e) && line(b, ib, q2s, q2e))) { perror("Error: Found read without sequence"); exit(1); }
+        out.push_back('>');
+        out.insert(out.end(), a.p + t1s, a.p + t1e);
+        out.push_back('\n');
+        out.insert(out.end(), a.p + q1s, a.p + q1e);
+        out.push_back('N');
+        out.insert(out.end(), b.p + q2s, b.p + q2e);
+        out.push_back('\n');
+        size_t x, y;                                     // '+' line and qualities of both mates
+        if (line(a, ia, x, y) && line(b, ib, x, y)) { if (line(a, ia, x, y) && line(b, ib, x, y)) continue; }
+    }
 }
 
 static bool is_single_input(const char* objects) {
@@ -398,12 +463,14 @@ static void run_single_end(Cli& c) {
 
 // src/CuCLARK_hh.hh:433-506
 static void run_paired_one(Cli& c, const char* f1, const char* f2, const char* result, bool list_mode) {
+    // the reference writes the joined mates to this file, classifies it and deletes it again (src/CuCLARK_hh.hh:443-451);
+    // here they stay in memory, the messages keep the name
     const string merged = string(f1) + "_ConcatenatedByCLARK.fa";
-    merge_paired_files(f1, f2, merged.c_str());
+    vector<char> joined;
+    merge_paired(f1, f2, joined);
     if (list_mode) cout << "> Processing file: '" << merged << "' in " << c.batches << " batches." << endl;
     else cout << "Processing file: '" << merged << "' in " << c.batches << " batches using " << c.cpu << " CPU thread(s)." << endl;
-    run_simple(c, merged.c_str(), result, true);
-    remove(merged.c_str());
+    run_simple(c, merged.c_str(), result, true, &joined);
 }
 
 static void run_paired_end(Cli& c) {

@@ -390,6 +390,30 @@ struct FileMap {
     }
 };
 
+// A FASTQ target (src/CuCLARK_hh.hh:986-1080 full variant, :769-860 light): the first line is skipped, the sequence
+// line is scanned, its newline resets the window and the next three lines ('+', qualities, the next header) are
+// skipped. The same k-mers come out of the FASTA scanner for the text ">\n<sequence line>\n" per record (a '>' line
+// is skipped and resets the window, :956-974), so a FASTQ target is rewritten into that form on the host.
+void fastq_target_as_fasta(const uint8_t* p, size_t n, std::vector<uint8_t>& out) {
+    out.clear();
+    out.reserve(n / 2 + 16);
+    size_t i = 0;
+    auto skip_line = [&] {
+        const uint8_t* nl = (const uint8_t*)memchr(p + i, '\n', n - i);
+        i = nl ? (size_t)(nl - p) + 1 : n;
+    };
+    skip_line();                                     // first header
+    while (i < n) {
+        const uint8_t* nl = (const uint8_t*)memchr(p + i, '\n', n - i);
+        const size_t e = nl ? (size_t)(nl - p) : n;
+        out.push_back('>'); out.push_back('\n');
+        out.insert(out.end(), p + i, p + e);
+        out.push_back('\n');
+        i = nl ? e + 1 : n;
+        skip_line(); skip_line(); skip_line();       // '+', qualities, next header
+    }
+}
+
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
@@ -635,6 +659,7 @@ extern "C" int cuclark_build_database(const cuclark_build_opts* o, const char* c
     void* keys = nullptr;
     uint16_t* labels = nullptr;
     FileScratch fs;
+    std::vector<uint8_t> fastq_text;
     auto cleanup = [&] {
         cudaFree(count); cudaFree(local); cudaFree(out_local); cudaFree(d_err); cudaFree(tile_base); cudaFree(out_tile);
         cudaFree(keys); cudaFree(labels);
@@ -662,13 +687,19 @@ extern "C" int cuclark_build_database(const cuclark_build_opts* o, const char* c
                 continue;
             }
             if (fm.n == 0) continue;
-            if (fm.p[0] != '>') {
-                set_error("%s: only FASTA targets are supported by the device builder (first byte '%c')", target_files[f], fm.p[0]);
+            const uint8_t* text = fm.p;
+            size_t text_n = fm.n;
+            if (fm.p[0] == '@') {                    // FASTQ target
+                fastq_target_as_fasta(fm.p, fm.n, fastq_text);
+                text = fastq_text.data(); text_n = fastq_text.size();
+                if (text_n == 0) continue;
+            } else if (fm.p[0] != '>') {
+                set_error("%s: targets must be FASTA or FASTQ files (first byte '%c'; spectrum files are not supported)", target_files[f], fm.p[0]);
                 cleanup();
                 return CUCLARK_ERR_FORMAT;
             }
             e.label = target_labels[f];
-            const int rc = scan_file(fs, fm.p, fm.n, k, o->light_gap, e, nullptr, &nt_pass, st);
+            const int rc = scan_file(fs, text, text_n, k, o->light_gap, e, nullptr, &nt_pass, st);
             if (rc) { cleanup(); return rc; }
             B(cudaStreamSynchronize(st));
         }

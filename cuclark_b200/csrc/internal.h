@@ -108,7 +108,7 @@ int synth_reads_launch(uint32_t seed, uint32_t genome_seed, uint32_t n_targets, 
                        uint64_t first_read, size_t n_reads, int read_len, int pct_random, int sub_per_10k,
                        uint32_t* d_ptr, uint16_t* d_cont, cudaStream_t st);
 int synth_fastq_launch(uint32_t seed, uint32_t genome_seed, uint32_t n_targets, uint64_t genome_len, uint64_t first_read,
-                       size_t n_reads, int read_len, int pct_random, int sub_per_10k, uint8_t* d_text, cudaStream_t st);
+                       size_t n_reads, int read_len, int pct_random, int sub_per_10k, uint8_t* d_text, cudaStream_t st, int mate = 0);
 // stream.cu
 void text_pipe_free(cuclark_db* db);
 

@@ -331,6 +331,12 @@ int cuclark_synth_fastq_device(cuclark_db* db, uint32_t seed, uint32_t genome_se
                                uint64_t genome_len, uint64_t first_read, size_t n_reads, int read_len,
                                int pct_random, int sub_per_10k, uint8_t* d_text, void* stream);
 
+/* The two files of a paired-end run (BASELINE configs[2]): mate = 1 writes the reads above, mate = 2 their mates —
+ * same id, same target, 2 x read_len further along, opposite strand, own substitutions. */
+int cuclark_synth_fastq_pair_device(cuclark_db* db, uint32_t seed, uint32_t genome_seed, uint32_t n_targets,
+                                    uint64_t genome_len, uint64_t first_read, size_t n_reads, int read_len,
+                                    int pct_random, int sub_per_10k, int mate, uint8_t* d_text, void* stream);
+
 /* ---- roofline probe: random 32-byte-sector gather over this table ---------- */
 /* Reads n_probes uniformly random sectors of the loaded table per launch
  * (ilp independent loads per thread); returns average ms over `iters` launches. */

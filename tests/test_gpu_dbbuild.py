@@ -145,12 +145,53 @@ def test_builder_edge_cases(tmp_path, gap, k, min_count):
         assert ky.size > 100          # the case is not trivially empty
 
 
+def fastq_as_fasta(data: bytes) -> bytes:
+    """A FASTQ target as the reference scans it (src/CuCLARK_hh.hh:986-1080; light :769-860): header line skipped,
+    sequence line scanned, its newline resets the window, three lines skipped. Equivalent FASTA text for scan_target."""
+    lines = data.split(b"\n")
+    if lines and lines[-1] == b"":
+        lines.pop()
+    return b"".join(b">\n" + lines[i] + b"\n" for i in range(1, len(lines), 4))
+
+
+def fastq_targets():
+    rng = np.random.default_rng(99)
+    seq = lambda n: rng.choice(np.frombuffer(b"ACGT", np.uint8), n).tobytes()
+    recs = lambda name, seqs: b"".join(b"@%s_%d some text\n%s\n+\n%s\n" % (name, i, s, b"I" * len(s)) for i, s in enumerate(seqs))
+    shared = seq(400)
+    f0 = recs(b"a", [seq(300), seq(26), seq(27), shared, seq(150) + b"N" + seq(90), seq(500).lower()])
+    f1 = recs(b"b", [seq(1000), shared[100:300], seq(40) + b"NNNN" + seq(41)])
+    f2 = recs(b"c", [seq(2500)])[:-1]                           # no trailing newline
+    f3 = (">fa_among_fastq\n%s\n" % seq(700).decode()).encode()
+    return [f0, f1, f2, f3], [0, 1, 2, 1]
+
+
+@pytest.mark.parametrize("gap,k", [(4, 27), (0, 27), (0, 31)])
+def test_builder_fastq_targets(tmp_path, gap, k):
+    """FASTQ target files (the reference accepts FASTA and FASTQ targets, src/CuCLARK_hh.hh:896-1112)."""
+    datas, labels = fastq_targets()
+    files = []
+    for i, d in enumerate(datas):
+        p = tmp_path / f"t{i}.fq"
+        p.write_bytes(d)
+        files.append(str(p))
+    hts = api.HTSIZE_LIGHT
+    kb = api.key_bytes_for(k, hts)
+    base = str(tmp_path / "db")
+    st = api.build_database(files, labels, base, k, light=bool(gap), light_gap=gap, htsize=hts)
+    as_fasta = [fastq_as_fasta(d) if d[:1] == b"@" else d for d in datas]
+    sz, ky, lb = expected_db(as_fasta, labels, k, gap, hts, kb)
+    gsz, gky, glb = read_files(base, hts, kb)
+    assert np.array_equal(gsz, sz) and np.array_equal(gky, ky) and np.array_equal(glb, lb)
+    assert st["n_kmers_kept"] == ky.size and ky.size > 50
+
+
 def test_builder_errors(tmp_path):
-    p = tmp_path / "reads.fq"
-    p.write_bytes(b"@r\nACGT\n+\nIIII\n")
+    p = tmp_path / "spectrum.txt"
+    p.write_bytes(b"ACGTACGTACGTACGTACGTACGTACG 5\n")
     with pytest.raises(api.CuclarkError) as e:
         api.build_database([str(p)], [0], str(tmp_path / "db"), 27, light=True)
-    assert e.value.code == -8 and "only FASTA targets" in str(e.value)
+    assert e.value.code == -8 and "FASTA or FASTQ" in str(e.value)
     with pytest.raises(api.CuclarkError):
         api.build_database([str(p)], [0], str(tmp_path / "db"), 33, light=True)
     # a missing target file is skipped as the reference does ("Failed to open"), an empty one adds nothing
