@@ -317,7 +317,8 @@ __global__ void __launch_bounds__(256) k_classify_dense(const ClassifyParams p, 
                     const int qn = w + j;
                     x = (x << 2) | ((c[qn >> 3] >> (2 * (7 - (qn & 7)))) & 3u);
                 }
-                const uint32_t label = table_lookup<LAYOUT>(p.t, canonical(x, k));
+                const uint64_t rc = revcomp2(x, k);
+                const uint32_t label = table_lookup<LAYOUT>(p.t, x <= rc ? x : rc, x <= rc);
                 if (label < p.n_targets) atomicAdd(&hist[label], 1u);
             }
         }
@@ -341,6 +342,10 @@ __global__ void k_merge_rows(const uint16_t* __restrict__ parts, int n_parts, ui
     uint16_t best = 0, sbest = 0, ib = 0, isb = 0, sum = 0;
     uint32_t n = 0;
     uint16_t* out = rows_out ? rows_out + (size_t)read * pitch : nullptr;
+    // an input row that was cut at row_pairs (its shard saw more targets than a row holds) makes the merged
+    // result of this read inexact: it is counted in truncated_rows, which callers must find zero
+    bool cut = false;
+    for (int g = 0; g < n_parts; g++) cut = cut || parts[g * part_stride + (size_t)read * pitch] > (uint16_t)row_pairs;
     for (;;) {
         uint32_t tmin = 0x10000u;
         for (int g = 0; g < n_parts; g++) {
@@ -364,8 +369,8 @@ __global__ void k_merge_rows(const uint16_t* __restrict__ parts, int n_parts, ui
     if (out) {
         out[0] = (uint16_t)n;
         for (uint32_t i = 1 + 2 * min(n, (uint32_t)row_pairs); i < (uint32_t)pitch; i++) out[i] = 0;
-        if (n > (uint32_t)row_pairs) atomicAdd(&counters[COUNTER_TRUNC], 1u);
     }
+    if (cut || (out && n > (uint32_t)row_pairs)) atomicAdd(&counters[COUNTER_TRUNC], 1u);
     if (final5) {
         uint16_t* f = final5 + (size_t)read * 5;
         f[0] = sum; f[1] = ib; f[2] = best; f[3] = isb; f[4] = sbest;

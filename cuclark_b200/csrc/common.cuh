@@ -391,12 +391,19 @@ __device__ __forceinline__ uint32_t ovf_lookup(const TableView& t, uint64_t c) {
 
 // Full lookup of one canonical k-mer (used by the slow paths; the hot kernel
 // inlines the same steps so that it can batch the home-sector loads).
+// `fwd`: the read showed the k-mer in its canonical form. It only matters for LOCAL tie k-mers (two possible homes,
+// possibly in two shards): the hot kernel takes the leftmost smallest hash in READ orientation, i.e. the rightmost
+// one of the canonical form when the read shows the other strand — the slow paths must pick the same home, so
+// that in a sharded table exactly one shard answers for such a k-mer whichever path a read takes on each shard.
 template <int LAYOUT>
-__device__ __forceinline__ uint32_t table_lookup(const TableView& t, uint64_t c) {
+__device__ __forceinline__ uint32_t table_lookup(const TableView& t, uint64_t c, bool fwd = true) {
     uint64_t q, b;
     if (LAYOUT == LAYOUT_LOCAL) {
         uint64_t sa, sb;
-        local_locate2(c, t.k, t.NL, t.line_lo, t.line_n, sa, sb, q);
+        int ol, orr;
+        local_min_offsets(c, t.k, ol, orr);
+        local_home_at(c, t.k - LOCAL_W + 1, t.NL, fwd ? ol : orr, sa, q);
+        sb = local_alt_sector(sa, q, t.line_lo, t.line_n);
         const uint64_t la = sa - t.lo;
         if (la >= t.n_local) return NO_LABEL;       // other shard
         const Sector A = load_sector(t.buckets + 2 * la), B = load_sector(t.buckets + 2 * (sb - t.lo));

@@ -254,3 +254,63 @@ def test_local_sampling_factor_and_batches(oracle, light_small, sfactor):
             assert np.array_equal(views[b][2][:hi - lo], final[lo:hi])
             assert np.array_equal(views[b][3][:hi - lo], rows[lo:hi])
         g.freeBatchMemory()
+
+
+def test_local_shards_ties_through_the_dense_path(oracle):
+    """Sharded LOCAL table + tie k-mers (periodic sequence: the smallest minimizer hash at two offsets, possibly homed in
+    two shards) + reads that hit more than 64 targets on SOME shards only (dense fallback there, fast path on the
+    others): exactly one shard must answer for every k-mer whichever path the read takes on each shard. Checked on the
+    per-shard hit totals (final[0]), which are exact on both paths: their sum over the shards is the oracle's total.
+    (The merged rows of such reads are cut at 63 pairs per shard and flagged in truncated_rows — see k_merge_rows.)"""
+    import torch
+    k, T, G = 21, 160, 1500
+    rng = np.random.default_rng(77)
+    targets = [synth.genome_codes(31, t, 0, G) for t in range(T)]
+    for t in range(T):                                           # every target carries a periodic stretch of its own
+        period = 2 + (t % 5)
+        unit = rng.integers(0, 4, period)
+        while len(set(unit.tolist())) < 2:
+            unit = rng.integers(0, 4, period)
+        targets[t][300:300 + 90] = np.resize(np.concatenate([unit, rng.integers(0, 4, 1 + t % 3)]), 90)
+    kmers, labels = dbtools.build_entries(targets, k, 0)
+    kb = key_bytes_for(k, HTSIZE_LIGHT)
+    sz, ky, lb = dbtools.entries_to_arrays(kmers, labels, HTSIZE_LIGHT, kb)
+    odb = oracle.db_from_arrays(HTSIZE_LIGHT, k, sz, ky, lb)
+    asc = np.frombuffer(b"ACGT", np.uint8)
+
+    def seg(t, a, n, rc):
+        c = targets[t][a:a + n]
+        return asc[(3 - c[::-1]) if rc else c].tobytes()
+    reads = []
+    for r in range(120):                                         # 60..76 targets per read: around the 64-slot limit
+        ts = rng.permutation(T)[:int(rng.integers(60, 77))]
+        reads.append(b">r%d\n" % r + b"".join(seg(int(t), 290, 110, bool(r & 1)) for t in ts) + b"\n")
+    for r in range(40):                                          # few targets: fast path everywhere
+        ts = rng.permutation(T)[:3]
+        reads.append(b">s%d\n" % r + b"N".join(seg(int(t), 280, 130, bool(r & 1)) for t in ts) + b"\n")
+    data = b"".join(reads)
+    ptr, cont, final, rows, lookups = oracle_expect(oracle, odb, k, data, T, 23)
+    n = ptr.size - 1
+    d_ptr = torch.from_numpy(ptr.astype(np.int32)).cuda()
+    d_cont = torch.from_numpy(cont.astype(np.int16)).cuda()
+    mixed = 0
+    for n_shards in (1, 3, 5):
+        total = np.zeros(n, np.int64)
+        dense_per_shard = []
+        for s in range(n_shards):
+            with CuClarkDB(k, T, htsize=HTSIZE_LIGHT, shard=(s, n_shards), layout=LOCAL) as g:
+                g.load_arrays(sz, ky, lb)
+                assert g.stats()["layout"] == LOCAL
+                d_final = torch.zeros((n, 5), dtype=torch.int16, device="cuda")
+                torch.cuda.synchronize()
+                g.classify_device(d_ptr.data_ptr(), d_cont.data_ptr(), n, d_final.data_ptr(), 0)
+                dense_per_shard.append(g.stats(sync=True)["dense_reads"])
+                torch.cuda.synchronize()
+                total += d_final.cpu().numpy().view(np.uint16)[:, 0].astype(np.int64)
+        bad = np.nonzero((total & 0xFFFF) != final[:, 0])[0]
+        assert bad.size == 0, (n_shards, bad[:5], total[bad[:5]], final[bad[:5], 0])
+        if n_shards > 1:
+            assert sum(dense_per_shard) > 0
+            mixed += len(set(dense_per_shard)) > 1               # some shards took more reads to the dense path than others
+    assert mixed >= 1
+    assert (final[:, 0] > 500).sum() >= 100
