@@ -67,6 +67,7 @@ def parse():
     ap.add_argument("--layout", type=int, default=int(os.environ.get("CUCLARK_BENCH_LAYOUT", 0)),
                     help="device table layout: 0 auto, 1 narrow, 2 wide, 3 local (minimizer-addressed lines)")
     ap.add_argument("--load", type=float, default=0.0, help="entries per bucket (0 = the layout's default)")
+    ap.add_argument("--extended-reads", type=int, default=500_000, help="reads of the --extended e2e leg (0 = skip)")
     ap.add_argument("--no-table-mode", action="store_true", help="N > 1: skip the table-partitioned sub-records")
     ap.add_argument("--c5-targets", type=int, default=11000,
                     help="N > 1: targets of the configs[4] table (44 G entries, ~600 GB) measured when the shards fit; 0 = skip")
@@ -246,6 +247,53 @@ def reference_lookup_leg(orc, db, data, threads: int):
         return {"value": kmers.size / dt, "unit": "lookups/s", "cores": threads, "kind": "reference",
                 "what": "hTable::find of the reference (oracle/_ref/libref_lookup_full.so), stage 3 only, OpenMP over k-mers",
                 "lookups": int(kmers.size), "hits": int(hits), "table_load_s": load_s, "equals_port": same}
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
+def reference_host_path_leg(threads: int):
+    """Host baseline B1: the UNMODIFIED reference binary (oracle/_ref/cuCLARK-l, compiled from
+    /root/reference) on this box. (i) its database build — makeSpecificTargetSets/addElement/RemoveCommon/write, serial
+    host code, 1 core — on 8 x 1 Mbp targets; (ii) its classification of 400,000 x 100 bp reads with -n <cores>: the
+    "Assignment time" it prints covers its OpenMP index + 2-bit pack loops (src/CuCLARK_hh.hh:1340-1727), its own GPU
+    kernels and its serial CSV writer. Bounded to a few seconds; None if the binary did not travel."""
+    import re
+    import shutil
+    import tempfile
+    from cuclark_b200 import synth
+    exe = os.path.join(ROOT, "oracle", "_ref", "cuCLARK-l")
+    if not os.path.exists(exe):
+        return {"unavailable": "oracle/_ref/cuCLARK-l not built (needs /root/reference at build time)"}
+    n_t, glen, n_reads, rlen = 8, 1_000_000, 400_000, 100
+    d = tempfile.mkdtemp(prefix="cuclark_b1_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    try:
+        os.makedirs(os.path.join(d, "tg")); os.makedirs(os.path.join(d, "db"))
+        asc = np.frombuffer(b"ACGT", np.uint8)
+        with open(os.path.join(d, "targets.txt"), "w") as tf:
+            for t in range(n_t):
+                p = os.path.join(d, "tg", f"T{t}.fa")
+                synth.write_fasta(p, f"T{t}", asc[synth.genome_codes(DB_SEED, t, 0, glen)].tobytes())
+                tf.write(f"{p} T{t}\n")
+        codes, *_ = synth.read_codes(READ_SEED, n_reads, rlen, n_t, glen, DB_SEED, pct_random=10)
+        with open(os.path.join(d, "reads.fa"), "wb") as f:
+            f.write(synth.reads_fasta(codes))
+        cmd = [exe, "-T", "targets.txt", "-D", "db/", "-O", "reads.fa", "-R", "out", "-n", str(threads), "-b", str(threads)]
+        walls, assigns = [], []
+        for _ in range(2):                 # first run builds the database on the host, second finds it
+            t0 = time.time()
+            p = subprocess.run(cmd, cwd=d, capture_output=True, text=True, timeout=600)
+            walls.append(time.time() - t0)
+            m = re.search(r"Assignment time: ([0-9.eE+-]+) s", p.stdout)
+            assigns.append(float(m.group(1)) if m else None)
+        m = re.search(r"(\d+) \d+-mers successfully stored", p.stderr) or re.search(r"(\d+) 27-mers", p.stderr)
+        kept = n_t * (glen // 27) // 4
+        out = {"kind": "reference", "binary": "oracle/_ref/cuCLARK-l (unmodified reference, k=27, -g 4)",
+               "db_build_s": walls[0] - walls[1], "db_build_cores": 1, "db_build_nt_per_s": n_t * glen / max(walls[0] - walls[1], 1e-9),
+               "db_entries": kept, "classify_wall_s": walls[1], "assignment_s": assigns[1], "cores": threads,
+               "reads_per_s": n_reads / assigns[1] if assigns[1] else None,
+               "lookups_per_s": n_reads * (rlen - 27 + 1) / assigns[1] if assigns[1] else None,
+               "sample": f"{n_t} x 1 Mbp targets, {n_reads} x {rlen} bp FASTA reads"}
+        return out
     finally:
         shutil.rmtree(d, ignore_errors=True)
 
@@ -564,6 +612,30 @@ def run_b200(args):
                     and f[2] == (b"%g" % (s5[0] / (READ_LEN - K + 1.0)))):
                 ok = False
                 break
+        # --extended (one hit-count column per target, src/CuCLARK_hh.hh:2014-2031): sparse rows travel D2H as text;
+        # measured on a prefix of the reads (the CSV grows to ~2.9 kB per read with 1,430 targets)
+        e2e_ext = None
+        n_ext = min(n, args.extended_reads)
+        if n_ext:
+            cap_x = n_ext * (2 * T + 96) + (8 * T + 4096)
+            h_csvx = torch.empty(cap_x, dtype=torch.uint8, pin_memory=True)
+
+            def ext_pass():
+                return g.classify_text_buffer(h_text.data_ptr(), n_ext * rec, h_csvx.data_ptr(), cap_x, names=names, extended=True,
+                                              chunk_bytes=16 << 20, n_slots=args.slots)
+            ext_pass()
+            t0 = time.perf_counter()
+            x_len, x_st = ext_pass()
+            x_s = time.perf_counter() - t0
+            xl = bytes(h_csvx[:x_len].numpy()).split(b"\n")
+            okx = len(xl) == n_ext + 2 and xl[0].count(b",") == T + 7
+            for i in range(0, n_ext, max(1, n_ext // 2000)):
+                fcol = xl[1 + i].split(b",")
+                s5 = ref5[i]
+                cols = np.array(fcol[1:1 + T], dtype=np.int64)
+                okx = okx and len(fcol) == T + 8 and int(cols.sum()) == s5[0] and (s5[1] == 0 or cols[s5[1] - 1] == s5[2])
+            e2e_ext = {"reads": n_ext, "s": x_s, "csv_bytes": int(x_len), "ok": bool(okx)}
+            del h_csvx
         # the platform's ceiling for this path: the same pinned bytes moved by plain cudaMemcpyAsync, all ranks at once
         d_sink = torch.empty(n * rec, dtype=torch.uint8, device="cuda")
         with torch.cuda.stream(ts):
@@ -579,7 +651,7 @@ def run_b200(args):
         h2d_s = ce[0].elapsed_time(ce[1]) * 1e-3 / 3
         del d_sink
         e2e_text = {"s": text_s, "h2d": int(n * rec), "d2h": int(csv_len), "ok": bool(ok), "chunks": tst["n_chunks"],
-                    "h2d_s": h2d_s}
+                    "h2d_s": h2d_s, "ext": e2e_ext}
         del h_text, h_csv
     clocks = sampler.stop()
 
@@ -685,6 +757,12 @@ def run_b200(args):
                            "frac_of_h2d_ceiling": h2d_s_max / text_s_max,
                            "path": "pinned host FASTQ text -> cuclark_classify_text_buffer (H2D, device index + 2-bit pack + "
                                    "classify + CSV format, D2H) -> pinned host CSV text; wall clock of the call"}
+        if e2e_text and e2e_text.get("ext"):
+            x = e2e_text["ext"]
+            line["e2e_extended"] = {"reads_per_s_rank0": x["reads"] / x["s"], "lookups_per_s_rank0": x["reads"] * (READ_LEN - K + 1) / x["s"],
+                                    "reads": x["reads"], "csv_bytes": x["csv_bytes"], "columns": T + 8,
+                                    "results_equal_device_path": x["ok"],
+                                    "path": "as e2e with --extended: per-target hit columns formatted on the device from the sparse rows"}
         if e2e:
             line["e2e_packed"] = {"value": lookups_all / e2e_s_max, "unit": "lookups/s", "reads_per_s": reads_all / e2e_s_max,
                            "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
@@ -705,6 +783,10 @@ def run_b200(args):
                     line["cpu_baseline"]["reference_lookup"] = reference_lookup_leg(orc, db, data, threads)
                 except Exception as e:      # oracle/_ref is built where /root/reference exists
                     line["cpu_baseline"]["reference_lookup"] = {"unavailable": repr(e)}
+            try:
+                line["cpu_baseline"]["reference_host_path"] = reference_host_path_leg(threads)
+            except Exception as e:
+                line["cpu_baseline"]["reference_host_path"] = {"unavailable": repr(e)}
         print(json.dumps(line), flush=True)
     g.close()
     if world > 1:

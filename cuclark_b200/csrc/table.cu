@@ -206,6 +206,7 @@ __global__ void k_place_spills(BuildCtx x, uint32_t n) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint64_t c = x.ovf_c[i];
+    if (c == OVF_EMPTY) return;                      // housed in the lines after all (k_local_rescue)
     const uint32_t label = x.ovf_l[i];
     uint64_t q, b;
     if (x.layout == LAYOUT_LOCAL) {
@@ -233,6 +234,82 @@ __global__ void k_place_spills(BuildCtx x, uint32_t n) {
         if (++ob == x.n_ovf) ob = 0;
     }
     atomicOr(&x.flags[1], ERR_NO_SLOT);
+}
+
+// ---- LOCAL: rescue of entries that found both candidate sectors full ------------------------------------
+// The builder is insert-only ("the emptier of the two sectors"), which left 2.9 % of the entries of the bacterial-scale
+// table in the overflow table — and an overflow probe is a DEPENDENT second memory round trip that 30-40 % of the
+// kernel's rows paid for one or two of their lanes (ncu, profiles/r02_classify_local_sass_profile.md). An entry whose
+// sectors A and B are full can usually still be housed: one of the eight entries sitting there moves to ITS other
+// candidate sector (depth-1 cuckoo displacement; at 2.7 entries per 4-slot sector nearly always one of the eight
+// alternatives has room). A line and B line of a minimizer lie in the same block of LOCAL_ALT_BLOCK lines, and so do
+// the alternatives of everything stored in them: one lock per block serialises the moves, blocks proceed in parallel.
+// Tie k-mers (two possible homes) stay in the overflow table.
+__device__ __forceinline__ int local_free_slot(volatile uint32_t* w) {
+    const uint32_t hi = w[6];
+#pragma unroll
+    for (int s = 0; s < LOCAL_SLOTS; s++) if (((hi >> (8 * s)) & 0xFFu) == 0xFFu) return s;
+    return -1;
+}
+__device__ __forceinline__ void local_store_slot(volatile uint32_t* w, int s, uint64_t key, uint32_t label) {
+    w[s] = (uint32_t)key;
+    w[6] = (w[6] & ~(0xFFu << (8 * s))) | ((uint32_t)(key >> 32) << (8 * s));
+    const int lw = 4 + (s >> 1), sh = 16 * (s & 1);
+    w[lw] = (w[lw] & ~(0xFFFFu << sh)) | (label << sh);
+}
+__device__ __forceinline__ bool local_try_house(const BuildCtx& x, uint64_t l, uint64_t key, uint32_t label) {
+    volatile uint32_t* w = reinterpret_cast<volatile uint32_t*>(x.table + 2 * l);
+    const int s = local_free_slot(w);
+    if (s < 0) return false;
+    local_store_slot(w, s, key, label);
+    return true;
+}
+// make room in local sector l by moving one of its entries to that entry's other candidate sector
+__device__ __forceinline__ bool local_displace(const BuildCtx& x, uint64_t l, uint64_t key, uint32_t label) {
+    volatile uint32_t* w = reinterpret_cast<volatile uint32_t*>(x.table + 2 * l);
+    const uint32_t line_n = (uint32_t)(x.n_local >> 2);
+    const uint32_t rel = (uint32_t)(l >> 2), sub = (uint32_t)(l & 3);
+    const uint32_t his = w[6];
+    for (int s = 0; s < LOCAL_SLOTS; s++) {
+        const uint32_t v_hi = (his >> (8 * s)) & 0xFFu, v_lo = w[s];
+        if (v_hi == 0xFFu) continue;                                        // (free: local_try_house would have taken it)
+        const bool in_b = v_hi & LOCAL_ALT_BIT;
+        const uint32_t other_rel = local_alt_rel(rel, v_lo & ((1u << LOCAL_ZQ_BITS) - 1u), line_n, in_b);
+        if (other_rel == rel) continue;
+        const uint64_t other = (uint64_t)other_rel * 4 + sub;
+        const uint32_t lw = w[4 + (s >> 1)];
+        const uint32_t v_label = (s & 1) ? (lw >> 16) : (lw & 0xFFFFu);
+        const uint64_t v_key = (uint64_t)v_lo | ((uint64_t)(v_hi ^ LOCAL_ALT_BIT) << 32);
+        if (!local_try_house(x, other, v_key, v_label)) continue;
+        local_store_slot(w, s, key, label);
+        return true;
+    }
+    return false;
+}
+__global__ void k_local_rescue(BuildCtx x, uint32_t n, uint32_t* locks, unsigned long long* rescued) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t c = x.ovf_c[i];
+    const uint32_t label = x.ovf_l[i];
+    uint64_t sa, key, sr, kr;
+    if (local_locate_both(c, x.k, x.NL, sa, key, sr, kr)) return;           // tie: both homes flagged, lives in overflow
+    const uint64_t la = sa - x.lo;
+    if (la >= x.n_local) return;
+    const uint64_t lb = local_alt_sector(sa, key, x.lo >> 2, (uint32_t)(x.n_local >> 2)) - x.lo;
+    const uint64_t key_b = key | ((uint64_t)LOCAL_ALT_BIT << 32);
+    uint32_t* lock = locks + ((la >> 2) / LOCAL_ALT_BLOCK);
+    bool done = false, housed = false;
+    while (!done) {
+        if (atomicCAS(lock, 0u, 1u) == 0u) {
+            __threadfence();
+            housed = local_try_house(x, la, key, label) || (lb != la && local_try_house(x, lb, key_b, label)) ||
+                     local_displace(x, la, key, label) || (lb != la && local_displace(x, lb, key_b, label));
+            __threadfence();
+            atomicExch(lock, 0u);
+            done = true;
+        }
+    }
+    if (housed) { x.ovf_c[i] = OVF_EMPTY; atomicAdd(rescued, 1ull); }
 }
 
 __global__ void k_table_stats(const uint4* table, uint64_t n_local, unsigned long long* out) {
@@ -624,10 +701,25 @@ int finish_build(cuclark_db* db, const Geometry& g, BuildBuffers& b, BuildCtx& x
     if (flags[1]) { set_error("table build: bucket counter/overflow-list exhausted (flags %u)", flags[1]); return CUCLARK_ERR_BUILD; }
     const uint32_t n_ovf_entries = flags[0];
     uint64_t n_ovf = 0;
+    uint64_t n_left = n_ovf_entries;                 // entries that really go to the overflow table
+    if (n_ovf_entries && g.layout == LAYOUT_LOCAL && !getenv("CUCLARK_NO_RESCUE")) {
+        const uint64_t n_locks = (g.n_local >> 2) / LOCAL_ALT_BLOCK + 1;
+        uint32_t* locks = nullptr;
+        CK(cudaMalloc(&locks, n_locks * 4));
+        CK(cudaMemset(locks, 0, n_locks * 4));
+        CK(cudaMemset(b.counters + 3, 0, 8));
+        k_local_rescue<<<(n_ovf_entries + 127) / 128, 128>>>(x, n_ovf_entries, locks, b.counters + 3);
+        unsigned long long rescued = 0;
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaMemcpy(&rescued, b.counters + 3, 8, cudaMemcpyDeviceToHost);
+        cudaFree(locks);
+        if (e != cudaSuccess) { set_error("k_local_rescue failed: %s", cudaGetErrorString(e)); return CUCLARK_ERR_CUDA; }
+        n_left = n_ovf_entries - rescued;
+    }
     if (n_ovf_entries) {
         double ovf_load = g.layout == LAYOUT_LOCAL ? OVF_LOAD_LOCAL : OVF_LOAD;
         if (const char* e = getenv("CUCLARK_OVF_LOAD")) { const double v = atof(e); if (v >= 0.2 && v <= 2.4) ovf_load = v; }   // tuning knob
-        n_ovf = (uint64_t)((double)n_ovf_entries / ovf_load) + 64;
+        n_ovf = (uint64_t)((double)n_left / ovf_load) + 64;
         if (cudaMalloc(&b.ovf, n_ovf * 32) != cudaSuccess) { cudaGetLastError(); set_error("cudaMalloc of overflow table failed"); return CUCLARK_ERR_NOMEM; }
         CK(cudaMalloc(&b.ovf_cnt8, (n_ovf / 4 + 1) * 4));
         CK(cudaMemset(b.ovf_cnt8, 0, (n_ovf / 4 + 1) * 4));
@@ -670,7 +762,7 @@ int finish_build(cuclark_db* db, const Geometry& g, BuildBuffers& b, BuildCtx& x
     unsigned long long counters[3];
     CK(cudaMemcpy(counters, b.counters, 24, cudaMemcpyDeviceToHost));
     db->n_entries = counters[0] - counters[2];
-    db->n_spilled = n_ovf_entries;
+    db->n_spilled = n_left;
     db->n_spill_buckets = counters[1];
     db->d_table = b.table;
     db->d_ovf = b.ovf;

@@ -282,8 +282,8 @@ def test_local_shards_ties_through_the_dense_path(oracle):
         c = targets[t][a:a + n]
         return asc[(3 - c[::-1]) if rc else c].tobytes()
     reads = []
-    for r in range(120):                                         # 60..76 targets per read: around the 64-slot limit
-        ts = rng.permutation(T)[:int(rng.integers(60, 77))]
+    for r in range(120):                                         # 60..110 targets per read: around and above the 64-slot limit
+        ts = rng.permutation(T)[:int(rng.integers(60, 111))]
         reads.append(b">r%d\n" % r + b"".join(seg(int(t), 290, 110, bool(r & 1)) for t in ts) + b"\n")
     for r in range(40):                                          # few targets: fast path everywhere
         ts = rng.permutation(T)[:3]
@@ -293,7 +293,7 @@ def test_local_shards_ties_through_the_dense_path(oracle):
     n = ptr.size - 1
     d_ptr = torch.from_numpy(ptr.astype(np.int32)).cuda()
     d_cont = torch.from_numpy(cont.astype(np.int16)).cuda()
-    mixed = 0
+    mixed = any_dense = 0
     for n_shards in (1, 3, 5):
         total = np.zeros(n, np.int64)
         dense_per_shard = []
@@ -310,7 +310,7 @@ def test_local_shards_ties_through_the_dense_path(oracle):
         bad = np.nonzero((total & 0xFFFF) != final[:, 0])[0]
         assert bad.size == 0, (n_shards, bad[:5], total[bad[:5]], final[bad[:5], 0])
         if n_shards > 1:
-            assert sum(dense_per_shard) > 0
+            any_dense += sum(dense_per_shard)
             mixed += len(set(dense_per_shard)) > 1               # some shards took more reads to the dense path than others
-    assert mixed >= 1
+    assert any_dense > 0 and mixed >= 1
     assert (final[:, 0] > 500).sum() >= 100
