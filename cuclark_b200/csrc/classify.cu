@@ -41,6 +41,9 @@ constexpr int ILP_ROUNDS = 4;         // independent probes per lane
 #ifndef CUCLARK_ILP_LOCAL
 #define CUCLARK_ILP_LOCAL 1
 #endif
+#ifndef CUCLARK_LOCAL_BRANCHFREE
+#define CUCLARK_LOCAL_BRANCHFREE 1
+#endif
 #ifndef CUCLARK_LOCAL_MIN_BLOCKS
 #define CUCLARK_LOCAL_MIN_BLOCKS 4
 #endif
@@ -236,14 +239,34 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, LAYOUT == LAYOUT_LOCAL ?
                                 live[j] = valid && lb64 < T.n_local;
                                 my_lookups += valid;
                                 const uint32_t rel_b = local_alt_rel(line - T.line_lo, zq, T.line_n, false);
+#if CUCLARK_LOCAL_BRANCHFREE
+                                // no branch around the loads: a lane without a k-mer (tail of a part, other shard) reads sector 0
+                                const uint64_t sa_ = live[j] ? (uint64_t)lb[j] : 0ull;
+                                const uint64_t sb_ = live[j] ? (uint64_t)rel_b * 4 + (uint64_t)(o_c & 3) : 0ull;
+                                sec[j] = load_sector_line(T.buckets + 2 * sa_);
+                                secb[j] = load_sector_line(T.buckets + 2 * sb_);
+#else
                                 if (live[j]) {
                                     sec[j] = load_sector_line(T.buckets + 2 * (uint64_t)lb[j]);
                                     secb[j] = load_sector_line(T.buckets + 2 * ((uint64_t)rel_b * 4 + (uint64_t)(o_c & 3)));
                                 }
+#endif
                             }
 #pragma unroll
                             for (int j = 0; j < ILP; j++) {
                                 uint32_t label = NO_LABEL;
+#if CUCLARK_LOCAL_BRANCHFREE
+                                {
+                                    const uint32_t la_ = match_sector<LAYOUT_LOCAL>(sec[j], q[j]);
+                                    const uint32_t lb_ = match_sector<LAYOUT_LOCAL>(secb[j], q[j] | ((uint64_t)LOCAL_ALT_BIT << 32));
+                                    label = la_ == NO_LABEL ? lb_ : la_;
+                                    // both candidate sectors full at build time: the k-mer may be in the overflow table
+                                    // (0.3 % of the entries after the builder's rescue pass): one warp-uniform branch
+                                    const bool ask_ovf = live[j] && label == NO_LABEL && sector_overflowed(sec[j]) && sector_overflowed(secb[j]);
+                                    if (__any_sync(0xFFFFFFFFu, ask_ovf)) { if (ask_ovf) label = ovf_lookup(T, cc[j]); }
+                                    if (!live[j] || label >= p.n_targets) label = NO_LABEL;
+                                }
+#else
                                 if (live[j]) {
                                     label = match_sector<LAYOUT_LOCAL>(sec[j], q[j]);
                                     if (label == NO_LABEL) label = match_sector<LAYOUT_LOCAL>(secb[j], q[j] | ((uint64_t)LOCAL_ALT_BIT << 32));
@@ -251,6 +274,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, LAYOUT == LAYOUT_LOCAL ?
                                     if (label == NO_LABEL && sector_overflowed(sec[j]) && sector_overflowed(secb[j])) label = ovf_lookup(T, cc[j]);
                                     if (label >= p.n_targets) label = NO_LABEL;
                                 }
+#endif
                                 hits.add(label, tkey, tcnt, lane);
                             }
                         } else {

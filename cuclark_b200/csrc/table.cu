@@ -264,25 +264,33 @@ __device__ __forceinline__ bool local_try_house(const BuildCtx& x, uint64_t l, u
     local_store_slot(w, s, key, label);
     return true;
 }
-// make room in local sector l by moving one of its entries to that entry's other candidate sector
-__device__ __forceinline__ bool local_displace(const BuildCtx& x, uint64_t l, uint64_t key, uint32_t label) {
+// make room in local sector l by moving one of its entries to that entry's other candidate sector; if that one is
+// full too, DEPTH more levels of the same (the entries of one sector often share their alternatives: they come in
+// clumps of a few minimizers, so one level left 0.33 % of the entries in the overflow table)
+template <int DEPTH>
+__device__ bool local_displace(const BuildCtx& x, uint64_t l, uint64_t key, uint32_t label, uint64_t from) {
     volatile uint32_t* w = reinterpret_cast<volatile uint32_t*>(x.table + 2 * l);
     const uint32_t line_n = (uint32_t)(x.n_local >> 2);
     const uint32_t rel = (uint32_t)(l >> 2), sub = (uint32_t)(l & 3);
-    const uint32_t his = w[6];
-    for (int s = 0; s < LOCAL_SLOTS; s++) {
-        const uint32_t v_hi = (his >> (8 * s)) & 0xFFu, v_lo = w[s];
-        if (v_hi == 0xFFu) continue;                                        // (free: local_try_house would have taken it)
-        const bool in_b = v_hi & LOCAL_ALT_BIT;
-        const uint32_t other_rel = local_alt_rel(rel, v_lo & ((1u << LOCAL_ZQ_BITS) - 1u), line_n, in_b);
-        if (other_rel == rel) continue;
-        const uint64_t other = (uint64_t)other_rel * 4 + sub;
-        const uint32_t lw = w[4 + (s >> 1)];
-        const uint32_t v_label = (s & 1) ? (lw >> 16) : (lw & 0xFFFFu);
-        const uint64_t v_key = (uint64_t)v_lo | ((uint64_t)(v_hi ^ LOCAL_ALT_BIT) << 32);
-        if (!local_try_house(x, other, v_key, v_label)) continue;
-        local_store_slot(w, s, key, label);
-        return true;
+    for (int pass = 0; pass < (DEPTH > 0 ? 2 : 1); pass++) {                // first the cheap moves, then the deeper ones
+        for (int s = 0; s < LOCAL_SLOTS; s++) {
+            const uint32_t v_hi = (w[6] >> (8 * s)) & 0xFFu, v_lo = w[s];
+            if (v_hi == 0xFFu) continue;                                    // (free: local_try_house would have taken it)
+            const bool in_b = v_hi & LOCAL_ALT_BIT;
+            const uint32_t other_rel = local_alt_rel(rel, v_lo & ((1u << LOCAL_ZQ_BITS) - 1u), line_n, in_b);
+            const uint64_t other = (uint64_t)other_rel * 4 + sub;
+            if (other == l || other == from) continue;
+            const uint32_t lw = w[4 + (s >> 1)];
+            const uint32_t v_label = (s & 1) ? (lw >> 16) : (lw & 0xFFFFu);
+            const uint64_t v_key = (uint64_t)v_lo | ((uint64_t)(v_hi ^ LOCAL_ALT_BIT) << 32);
+            bool moved;
+            if (pass == 0) moved = local_try_house(x, other, v_key, v_label);
+            else if constexpr (DEPTH > 0) moved = local_displace<DEPTH - 1>(x, other, v_key, v_label, l);
+            else moved = false;
+            if (!moved) continue;
+            local_store_slot(w, s, key, label);
+            return true;
+        }
     }
     return false;
 }
@@ -303,7 +311,7 @@ __global__ void k_local_rescue(BuildCtx x, uint32_t n, uint32_t* locks, unsigned
         if (atomicCAS(lock, 0u, 1u) == 0u) {
             __threadfence();
             housed = local_try_house(x, la, key, label) || (lb != la && local_try_house(x, lb, key_b, label)) ||
-                     local_displace(x, la, key, label) || (lb != la && local_displace(x, lb, key_b, label));
+                     local_displace<2>(x, la, key, label, ~0ull) || (lb != la && local_displace<2>(x, lb, key_b, label, ~0ull));
             __threadfence();
             atomicExch(lock, 0u);
             done = true;
