@@ -293,6 +293,8 @@ def reference_host_path_leg(threads: int):
                "reads_per_s": n_reads / assigns[1] if assigns[1] else None,
                "lookups_per_s": n_reads * (rlen - 27 + 1) / assigns[1] if assigns[1] else None,
                "sample": f"{n_t} x 1 Mbp targets, {n_reads} x {rlen} bp FASTA reads"}
+        if assigns[1] is None:
+            out["output_tail"] = (p.stdout + p.stderr)[-600:]
         return out
     finally:
         shutil.rmtree(d, ignore_errors=True)
