@@ -42,15 +42,20 @@ static int use_device(cuclark_db* db) {
 }
 
 static void free_scratch(Scratch& sc) {
-    cudaFree(sc.d_counters); cudaFree(sc.d_dense_list);
+    cudaFree(sc.d_counters); cudaFree(sc.d_dense_list); cudaFree(sc.d_dense_hist);
     sc = Scratch{};
 }
 
-static int alloc_scratch(Scratch& sc, uint32_t dense_cap) {
+// hist_words > 0: the scratch gets its own dense-fallback histogram (dense_blocks * n_targets counters)
+static int alloc_scratch(Scratch& sc, uint32_t dense_cap, size_t hist_words = 0) {
     sc.dense_cap = dense_cap;
     CK(cudaMalloc(&sc.d_counters, N_COUNTERS * sizeof(uint32_t)));
     CK(cudaMalloc(&sc.d_dense_list, (size_t)dense_cap * 4));
     CK(cudaMemset(sc.d_counters, 0, N_COUNTERS * sizeof(uint32_t)));
+    if (hist_words) {
+        CK(cudaMalloc(&sc.d_dense_hist, hist_words * 4));
+        CK(cudaMemset(sc.d_dense_hist, 0, hist_words * 4));
+    }
     return CUCLARK_OK;
 }
 
@@ -277,7 +282,7 @@ int cuclark_batches_alloc(cuclark_db* db, int n_batches, size_t max_reads, size_
     for (auto& b : db->batches) {
         CK(cudaStreamCreateWithFlags(&b.stream, cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&b.done, cudaEventDisableTiming));
-        rc = alloc_scratch(b.scratch, 1u << 18);
+        rc = alloc_scratch(b.scratch, 1u << 18, (size_t)db->dense_blocks * db->cfg.n_targets);
         if (rc) return rc;
         CK(cudaMallocHost(&b.h_counters, N_COUNTERS * sizeof(uint32_t)));
         CK(cudaMallocHost(&b.h_ptr, (max_reads + 1) * 4));

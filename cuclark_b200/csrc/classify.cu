@@ -564,15 +564,23 @@ int classify_launch(cuclark_db* db, const Scratch& sc, const uint32_t* d_ptr, co
     const int blocks = std::min(blocks_needed, db->sm_count * db->classify_blocks_per_sm[variant]);
     kern<<<blocks, WARPS_PER_BLOCK * 32, 0, st>>>(p);
     CK(cudaGetLastError());
-    // exact fallback; exits at once when the list is empty. Its histogram
-    // scratch is shared, so dense kernels are chained across streams.
-    std::lock_guard<std::mutex> dense_guard(db->dense_mu);
-    CK(cudaStreamWaitEvent(st, db->dense_chain, 0));
-    if (narrow) k_classify_dense<LAYOUT_NARROW><<<db->dense_blocks, 256, 0, st>>>(p, db->d_dense_hist);
-    else if (local) k_classify_dense<LAYOUT_LOCAL><<<db->dense_blocks, 256, 0, st>>>(p, db->d_dense_hist);
-    else k_classify_dense<LAYOUT_WIDE><<<db->dense_blocks, 256, 0, st>>>(p, db->d_dense_hist);
-    CK(cudaGetLastError());
-    CK(cudaEventRecord(db->dense_chain, st));
+    // exact fallback; exits at once when the list is empty. A scratch with its own histogram (batches, pipeline slots)
+    // makes the call independent of every other stream; the handle's shared one is chained across streams.
+    auto dense = [&](uint32_t* hist) {
+        if (narrow) k_classify_dense<LAYOUT_NARROW><<<db->dense_blocks, 256, 0, st>>>(p, hist);
+        else if (local) k_classify_dense<LAYOUT_LOCAL><<<db->dense_blocks, 256, 0, st>>>(p, hist);
+        else k_classify_dense<LAYOUT_WIDE><<<db->dense_blocks, 256, 0, st>>>(p, hist);
+    };
+    if (sc.d_dense_hist) {
+        dense(sc.d_dense_hist);
+        CK(cudaGetLastError());
+    } else {
+        std::lock_guard<std::mutex> dense_guard(db->dense_mu);
+        CK(cudaStreamWaitEvent(st, db->dense_chain, 0));
+        dense(db->d_dense_hist);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(db->dense_chain, st));
+    }
     count_launches(2);
     return CUCLARK_OK;
 }

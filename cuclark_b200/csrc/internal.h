@@ -22,6 +22,8 @@ struct Scratch {
     uint32_t* d_counters = nullptr;    // N_COUNTERS
     uint32_t* d_dense_list = nullptr;
     uint32_t dense_cap = 0;
+    uint32_t* d_dense_hist = nullptr;  // dense_blocks * n_targets counters of the dense fallback, all zero between calls.
+                                       // Every batch / pipeline slot has its own, so calls on different streams are independent
 };
 
 struct Batch {
@@ -61,8 +63,8 @@ struct cuclark_db {
     uint64_t src_mtime_ns[3] = {0, 0, 0};
     // classify scratch (one-shot calls; batches carry their own)
     cuclark::Scratch scratch;
-    uint32_t* d_dense_hist = nullptr;  // dense_blocks * n_targets, shared: dense kernels are
-    cudaEvent_t dense_chain = nullptr; //   serialised across streams through this event
+    uint32_t* d_dense_hist = nullptr;  // dense_blocks * n_targets, for callers whose Scratch has none: those dense kernels
+    cudaEvent_t dense_chain = nullptr; //   are serialised across streams through this event
     std::mutex dense_mu;               //   (wait + launch + record must not interleave between host threads)
     int dense_blocks = 0;
     int classify_blocks_per_sm[6] = {0, 0, 0, 0, 0, 0};

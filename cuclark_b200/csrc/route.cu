@@ -653,11 +653,16 @@ int route_gather(cuclark_db* db, const Scratch& sc, const uint32_t* d_ptr, const
     if (d_rows) k_route_gather<true><<<blocks, R_WARPS * 32, 0, st>>>(p);
     else k_route_gather<false><<<blocks, R_WARPS * 32, 0, st>>>(p);
     CK(cudaGetLastError());
-    std::lock_guard<std::mutex> dense_guard(db->dense_mu);
-    CK(cudaStreamWaitEvent(st, db->dense_chain, 0));
-    k_route_dense<<<db->dense_blocks, 256, 0, st>>>(p, db->d_dense_hist);
-    CK(cudaGetLastError());
-    CK(cudaEventRecord(db->dense_chain, st));
+    if (sc.d_dense_hist) {
+        k_route_dense<<<db->dense_blocks, 256, 0, st>>>(p, sc.d_dense_hist);
+        CK(cudaGetLastError());
+    } else {
+        std::lock_guard<std::mutex> dense_guard(db->dense_mu);
+        CK(cudaStreamWaitEvent(st, db->dense_chain, 0));
+        k_route_dense<<<db->dense_blocks, 256, 0, st>>>(p, db->d_dense_hist);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(db->dense_chain, st));
+    }
     count_launches(2);
     return CUCLARK_OK;
 }

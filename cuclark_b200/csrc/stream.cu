@@ -76,7 +76,7 @@ struct Carver {
 // Pinned memory costs ~0.6 ms per MiB to allocate on the B200 host (16 slots of 64 MiB chunks took
 // 3.6 s, the classification of 2 M reads 40 ms), so a slot is sized tightly and allocated by its own
 // thread while the other slots already work. `with_stage`: the source is pageable and needs h_text.
-int alloc_slot(TextSlot& s, size_t C, bool extended, int row_pairs, bool with_stage) {
+int alloc_slot(TextSlot& s, size_t C, bool extended, int row_pairs, bool with_stage, size_t hist_words) {
     TextSlotDev& d = s.d;
     d.cap_bytes = C;
     d.cap_lines = C / 6 + 64;
@@ -103,6 +103,7 @@ int alloc_slot(TextSlot& s, size_t C, bool extended, int row_pairs, bool with_st
         c.take(d.info, 1);
         c.take(s.scratch.d_counters, (size_t)N_COUNTERS);
         c.take(s.scratch.d_dense_list, (size_t)s.scratch.dense_cap);
+        c.take(s.scratch.d_dense_hist, hist_words);          // the slot's own dense-fallback histogram: no cross-stream chain
     };
     auto carve_host = [&](Carver& c) {
         c.take(s.h_info, 1);
@@ -120,6 +121,7 @@ int alloc_slot(TextSlot& s, size_t C, bool extended, int row_pairs, bool with_st
     CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     CK(cudaMemsetAsync(d.text, '\n', C + 256, s.stream));
     CK(cudaMemsetAsync(s.scratch.d_counters, 0, N_COUNTERS * sizeof(uint32_t), s.stream));
+    CK(cudaMemsetAsync(s.scratch.d_dense_hist, 0, hist_words * 4, s.stream));
     return CUCLARK_OK;
 }
 
@@ -343,7 +345,7 @@ void worker(Job& J, cuclark_db* db, TextSlot& S) {
         int rc;
         {
             std::lock_guard<std::mutex> g(alloc_mu);
-            rc = alloc_slot(S, tp->chunk_bytes, tp->extended, tp->row_pairs, !J.src_pinned);
+            rc = alloc_slot(S, tp->chunk_bytes, tp->extended, tp->row_pairs, !J.src_pinned, (size_t)db->dense_blocks * db->cfg.n_targets);
         }
         if (rc) { free_slot(S); J.fail(rc, cuclark_last_error()); return; }
         pc.lap(6);
@@ -380,7 +382,7 @@ void worker(Job& J, cuclark_db* db, TextSlot& S) {
             std::lock_guard<std::mutex> g(grow_mu);
             const bool stage = S.with_stage;
             free_slot(S);
-            const int rc = alloc_slot(S, ((size_t)nb + (1u << 20)) & ~(size_t)255, tp->extended, tp->row_pairs, stage);
+            const int rc = alloc_slot(S, ((size_t)nb + (1u << 20)) & ~(size_t)255, tp->extended, tp->row_pairs, stage, (size_t)db->dense_blocks * db->cfg.n_targets);
             if (rc) { free_slot(S); J.fail(rc, cuclark_last_error()); return; }
         }
         const uint8_t* src = J.text + start;
@@ -498,7 +500,7 @@ void worker_routed(Job& J, cuclark_db* const* dbs, int g) {
     if (!S.stream) {
         static std::mutex alloc_mu;
         std::lock_guard<std::mutex> lk(alloc_mu);
-        const int rc = alloc_slot(S, tp->chunk_bytes, tp->extended, tp->row_pairs, !J.src_pinned);
+        const int rc = alloc_slot(S, tp->chunk_bytes, tp->extended, tp->row_pairs, !J.src_pinned, (size_t)db->dense_blocks * db->cfg.n_targets);
         if (rc) { free_slot(S); J.fail(rc, cuclark_last_error()); return; }
     }
     const TextSlotDev& d = S.d;
