@@ -342,7 +342,7 @@ def workload_config(args, world):
             "l2_policy": "inputs larger than L2 (packed reads 400 MB, table >> 126 MB); no flush needed"}
 
 
-def run_table_mode(args, rank, world, local, targets, d_ptr, d_cont, n, ts, ref_final=None, steps=None):
+def run_table_mode(args, rank, world, local, targets, d_ptr, d_cont, n, ts, ref_final=None, steps=None, layout=0):
     """Table-partitioned run of the SAME reads: rank r holds shard r of the table (hashed sectors) and its own reads;
     k-mers travel to their shard and labels come back over NVLink inside the probe kernel (csrc/route.cu), with two
     stream-ordered NCCL all-reduces of one float as the barriers between scatter | probe | gather."""
@@ -353,7 +353,7 @@ def run_table_mode(args, rank, world, local, targets, d_ptr, d_cont, n, ts, ref_
     steps = steps or args.steps
     per = 1 + (READ_LEN + 7) // 8
     stream = ts.cuda_stream
-    g = CuClarkDB(K, targets, htsize=HTSIZE_FULL, device=local, shard=(rank, world))
+    g = CuClarkDB(K, targets, htsize=HTSIZE_FULL, device=local, shard=(rank, world), layout=layout)
     t0 = time.time()
     g.build_synthetic(DB_SEED, targets, GENOME_LEN, 0)
     build_s = time.time() - t0
@@ -435,13 +435,16 @@ def run_table_mode(args, rank, world, local, targets, d_ptr, d_cont, n, ts, ref_
             "targets": targets, "table_bytes_all_shards": table_bytes, "table_bytes_per_gpu": table_bytes / world,
             "layout": {1: "narrow", 2: "wide", 3: "local"}.get(st["layout"]), "shard_build_s": build_s,
             "lookups_per_step": lookups_all, "probed_per_step": probed_all,
-            "nvlink_bytes_per_lookup": blocks_remote * 256 * 10 / max(lookups_all, 1.0),
+            "nvlink_bytes_per_lookup": blocks_remote * 256 * (14 if st["layout"] == 3 else 10) / max(lookups_all, 1.0),
             "routing_buffers_bytes_per_gpu": rs["region_bytes"] + rs["map_bytes"],
             "rows_equal_read_partitioned": (differ == 0) if ref_final is not None else None,
             "rows_equal_ground_truth": bool(bad_all <= bound * world), "ground_truth_mismatches": int(bad_all),
             "gpu_launches_per_rank": launches, "route_err": int(err), "phase_ms_rank0": phase_ms,
-            "path": "reads partitioned, table partitioned by bucket range; k_route_scatter | all-reduce | k_route_probe "
-                    "(peer loads of k-mers, peer stores of labels over NVLink) | all-reduce | k_route_gather"}
+            "overflow_entries_this_shard": st["n_spilled"],
+            "path": "reads partitioned, table partitioned by " + ("line range (LOCAL shards: minimizer lines, entries = sector + key, 12 B)"
+                                                                   if st["layout"] == 3 else "bucket range (hashed shards, entries = k-mer, 8 B)") +
+                    "; k_route_scatter | all-reduce | k_route_probe_tma (TMA pulls of the peers' blocks, peer stores of labels "
+                    "over NVLink) | all-reduce | k_route_gather"}
 
 
 # ---------------------------------------------------------------- GPU arm
@@ -702,7 +705,10 @@ def run_b200(args):
     if world > 1 and not table_mode and not args.no_table_mode:
         g.close()
         torch.cuda.empty_cache()
-        table_records["table_mode"] = run_table_mode(args, rank, world, local, T, d_ptr, d_cont, n, ts, ref_final=f)
+        # config 2's table as LOCAL shards (it fits the 2^30-line bound of that layout) and as hashed shards (any size)
+        table_records["table_mode"] = run_table_mode(args, rank, world, local, T, d_ptr, d_cont, n, ts, ref_final=f, layout=3)
+        table_records["table_mode_hashed"] = run_table_mode(args, rank, world, local, T, d_ptr, d_cont, n, ts, ref_final=f,
+                                                            steps=max(2, args.steps // 2))
         # BASELINE configs[4]: a table that exceeds one GPU (11,000 targets = 44 G entries, ~600 GB over the shards)
         free_b = torch.cuda.mem_get_info()[0]
         c5_targets = args.c5_targets

@@ -20,8 +20,13 @@
 // Between the steps all ranks meet at a barrier (the caller's: stream-ordered NCCL all-reduce under torchrun,
 // CUDA events between the devices of one process). NVLink carries 8 bytes per k-mer one way and 2 bytes back.
 // Because a canonical k-mer has exactly one home shard the labels, and so every count, equal the single-table
-// result bit for bit. Hashed table layouts only (NARROW / WIDE); the single-device LOCAL layout does not shard
-// at bacterial scale (its line count is bound to 2^30).
+// result bit for bit.
+// Table layouts: hashed shards (NARROW / WIDE: any table size; the arena entry is the canonical k-mer, the owner is the
+// shard of its home bucket) and LOCAL shards (tables of up to 2^30 lines in all, i.e. config-2 scale: the scatter
+// kernel runs the minimizer front end, the owner is the shard of the A line, the arena entry is (sector, 37-bit key);
+// consecutive k-mers of a read share their minimizer, so they land next to each other in the owner's block and its
+// probes coalesce into line requests exactly as in the single-table kernel — a probe costs ~0.44 line requests
+// instead of one random sector).
 #include <stdlib.h>
 #include <string.h>
 
@@ -30,6 +35,7 @@
 #include "hits.cuh"
 #include "internal.h"
 #include "kmerwin.cuh"
+#include "local_rows.cuh"
 
 namespace cuclark {
 
@@ -61,8 +67,9 @@ __host__ __device__ inline size_t align256(size_t x) { return (x + 255) & ~(size
 struct RegionView {
     RouteHeader* hdr;
     uint32_t* blocklist;                          // [n_ranks][cap_blocks]
-    uint64_t* arena;                              // [cap_blocks * BLK]
+    uint64_t* arena;                              // [cap_blocks * BLK]: canonical k-mers (hashed shards) or slot keys (LOCAL shards)
     uint16_t* labels;                             // [cap_blocks * BLK]
+    uint32_t* sec32;                              // [cap_blocks * BLK], LOCAL shards: A sector of the entry, relative to its owner's shard
 };
 __host__ __device__ inline RegionView region_view(uint8_t* base, int n_ranks, uint32_t cap_blocks) {
     RegionView v;
@@ -70,14 +77,16 @@ __host__ __device__ inline RegionView region_view(uint8_t* base, int n_ranks, ui
     v.hdr = reinterpret_cast<RouteHeader*>(base); off = align256(sizeof(RouteHeader));
     v.blocklist = reinterpret_cast<uint32_t*>(base + off); off = align256(off + (size_t)n_ranks * cap_blocks * 4);
     v.arena = reinterpret_cast<uint64_t*>(base + off); off = align256(off + (size_t)cap_blocks * BLK * 8);
-    v.labels = reinterpret_cast<uint16_t*>(base + off);
+    v.labels = reinterpret_cast<uint16_t*>(base + off); off = align256(off + (size_t)cap_blocks * BLK * 2);
+    v.sec32 = reinterpret_cast<uint32_t*>(base + off);
     return v;
 }
-size_t region_bytes(int n_ranks, uint32_t cap_blocks) {
+size_t region_bytes(int n_ranks, uint32_t cap_blocks, bool with_sec) {
     size_t off = align256(sizeof(RouteHeader));
     off = align256(off + (size_t)n_ranks * cap_blocks * 4);
     off = align256(off + (size_t)cap_blocks * BLK * 8);
     off = align256(off + (size_t)cap_blocks * BLK * 2);
+    if (with_sec) off = align256(off + (size_t)cap_blocks * BLK * 4);
     return off;
 }
 
@@ -88,8 +97,10 @@ struct ScatterParams {
     int k;
     uint64_t M, magic;                            // the GLOBAL bucket count of the sharded table
     int n_ranks;
-    uint64_t lo[ROUTE_MAX_RANKS + 1];             // shard i holds home buckets [lo[i], lo[i+1])
-    float inv_width;                              // n_ranks / M, for the owner estimate
+    uint64_t lo[ROUTE_MAX_RANKS + 1];             // shard i holds home buckets [lo[i], lo[i+1]) (LOCAL: lines)
+    float inv_width;                              // n_ranks / M (LOCAL: / NL), for the owner estimate
+    uint32_t NL, nl_m32;                          // LOCAL: the GLOBAL line count and the constants of local_divmod()
+    int nl_sh;
     RegionView mine;
     uint32_t cap_blocks;
     uint32_t* pos_of;                             // [8 * n_cont]: arena index of the k-mer at (container, nucleotide)
@@ -104,6 +115,7 @@ __device__ __forceinline__ int owner_of(const ScatterParams& p, uint64_t b) {
 }
 
 // ---- scatter: k-mers of this rank's reads into per-owner blocks of the local arena -------------------------
+template <bool LOCAL>
 __global__ void __launch_bounds__(R_WARPS * 32, SCATTER_BLOCKS_PER_SM) k_route_scatter(const ScatterParams p) {
     __shared__ uint32_t s_base[R_WARPS][ROUTE_MAX_RANKS];     // arena index of the owner's open block
     __shared__ uint32_t s_used[R_WARPS][ROUTE_MAX_RANKS];     // entries used in it (BLK = none open)
@@ -150,14 +162,28 @@ __global__ void __launch_bounds__(R_WARPS * 32, SCATTER_BLOCKS_PER_SM) k_route_s
                     }
                     const uint64_t W = assemble_words(wv, nwin, lane);
                     const int rounds = min(CHUNK_ROUNDS, (nk - cb + 31) >> 5);
+                    LocalCarry carry;                        // LOCAL: hash row handed over from the previous round
+                    const int m_limit = (int)L - (k - LOCAL_W + 1) - cb - lane;
                     for (int i = 0; i < rounds; i++) {
-                        const uint64_t hi = shfl64(W, i & 31), lo = shfl64(W, (i + 1) & 31);
-                        const uint64_t c = canonical(window64(hi, lo, 2 * lane) >> kshift, k);
                         const int w = cb + 32 * i + lane;
                         const bool valid = w < nk;
-                        uint64_t q, b;
-                        divmod_M(c, p.M, p.magic, q, b);
-                        const int d = valid ? owner_of(p, b) : -1;
+                        uint64_t entry;                      // what the owner needs: the k-mer, or (LOCAL) its slot key ...
+                        uint32_t entry_sec = 0;              // ... and its A sector inside the owner's shard
+                        int d = -1;
+                        if (LOCAL) {
+                            const LocalProbe P = local_row(carry, W, i, m_limit, k, kshift, p.NL, p.nl_m32, p.nl_sh, lane);
+                            if (valid) {
+                                d = owner_of(p, (uint64_t)P.line);
+                                entry_sec = (uint32_t)(((uint64_t)P.line - p.lo[d]) * 4 + (uint64_t)(P.o_c & 3));
+                            }
+                            entry = P.key;
+                        } else {
+                            const uint64_t hi = shfl64(W, i & 31), lo = shfl64(W, (i + 1) & 31);
+                            entry = canonical(window64(hi, lo, 2 * lane) >> kshift, k);
+                            uint64_t q, b;
+                            divmod_M(entry, p.M, p.magic, q, b);
+                            if (valid) d = owner_of(p, b);
+                        }
                         my_lookups += valid;
                         // lanes with the same owner take consecutive entries of that owner's open block
                         const uint32_t grp = __match_any_sync(0xFFFFFFFFu, d);
@@ -185,7 +211,8 @@ __global__ void __launch_bounds__(R_WARPS * 32, SCATTER_BLOCKS_PER_SM) k_route_s
                         }
                         at = __shfl_sync(0xFFFFFFFFu, at, leader < 0 ? 0 : leader) + __popc(grp & lt);
                         if (valid) {
-                            p.mine.arena[at] = c;
+                            p.mine.arena[at] = entry;
+                            if (LOCAL) p.mine.sec32[at] = entry_sec;
                             p.pos_of[8u * first + (uint32_t)w] = at;
                         }
                         __syncwarp();
@@ -245,6 +272,41 @@ __device__ __forceinline__ void probe_block(const ProbeParams& p, const uint64_t
     }
 }
 
+// The same for a LOCAL shard: the entry is (A sector inside this shard, 37-bit key). Consecutive entries of a block
+// come from consecutive k-mers of a read, share their minimizer and so their two candidate lines: the 32 lanes'
+// loads of one round coalesce into ~14 line requests. Two entries per lane in flight (2 x 2 sectors of registers).
+__device__ __forceinline__ void probe_block_local(const ProbeParams& p, const uint64_t (&key)[BLK / 32], const uint32_t (&sa)[BLK / 32],
+                                                  uint16_t* dst, int lane, unsigned long long& probed) {
+    const TableView& T = p.t;
+#pragma unroll
+    for (int h = 0; h < (int)(BLK / 32); h += 2) {
+        Sector A[2], B[2];
+        bool live[2];
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            live[j] = key[h + j] != SENTINEL && (uint64_t)sa[h + j] < T.n_local;
+            const uint32_t a = live[j] ? sa[h + j] : 0u;                 // lanes without an entry read sector 0
+            const uint32_t zq = (uint32_t)key[h + j] & ((1u << LOCAL_ZQ_BITS) - 1u);
+            const uint32_t b = live[j] ? local_alt_rel(a >> 2, zq, T.line_n, false) * 4u + (a & 3u) : 0u;
+            A[j] = load_sector_line(T.buckets + 2 * (uint64_t)a);
+            B[j] = load_sector_line(T.buckets + 2 * (uint64_t)b);
+        }
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const uint32_t la = match_sector<LAYOUT_LOCAL>(A[j], key[h + j]);
+            const uint32_t lb = match_sector<LAYOUT_LOCAL>(B[j], key[h + j] | ((uint64_t)LOCAL_ALT_BIT << 32));
+            uint32_t label = la == NO_LABEL ? lb : la;
+            const bool ask_ovf = live[j] && label == NO_LABEL && sector_overflowed(A[j]) && sector_overflowed(B[j]);
+            if (__any_sync(0xFFFFFFFFu, ask_ovf)) {
+                if (ask_ovf) label = ovf_lookup(T, local_rebuild((uint64_t)T.line_lo + (sa[h + j] >> 2), key[h + j], T.k, T.NL));
+            }
+            if (!live[j] || label >= p.n_targets) label = NO_LABEL;
+            probed += live[j];
+            dst[32 * (h + j) + lane] = label == NO_LABEL ? LABEL_NONE : (uint16_t)label;
+        }
+    }
+}
+
 // Every warp walks its share of the block list addressed to this shard in rank g's region. The k-mers of the NEXT
 // block (and the list entry after it) are already on their way over NVLink while the current block is probed:
 // a remote load takes microseconds, and without the prefetch the probe rate fell from 33 G/s (2 GPUs, half of the
@@ -296,8 +358,10 @@ __global__ void __launch_bounds__(256, 2) k_route_probe(const ProbeParams p) {
 // with one coalesced load.
 constexpr int PROBE_STAGES = 4;
 constexpr int PROBE_WARPS = 8;
+template <bool LOCAL>
 struct alignas(128) ProbeWarpSmem {
     uint64_t kmers[PROBE_STAGES][BLK];
+    uint32_t secs[LOCAL ? PROBE_STAGES : 1][LOCAL ? BLK : 4];
     uint64_t bar[PROBE_STAGES];
 };
 
@@ -324,7 +388,8 @@ template <int LAYOUT>
 __global__ void __launch_bounds__(PROBE_WARPS * 32, 2) k_route_probe_tma(const ProbeParams p) {
     extern __shared__ __align__(128) uint8_t probe_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    ProbeWarpSmem& S = reinterpret_cast<ProbeWarpSmem*>(probe_smem)[wib];
+    constexpr bool LOCAL = LAYOUT == LAYOUT_LOCAL;
+    ProbeWarpSmem<LOCAL>& S = reinterpret_cast<ProbeWarpSmem<LOCAL>*>(probe_smem)[wib];
     if (lane == 0)
         for (int s = 0; s < PROBE_STAGES; s++) mbar_init(&S.bar[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -347,8 +412,9 @@ __global__ void __launch_bounds__(PROBE_WARPS * 32, 2) k_route_probe_tma(const P
                 const uint32_t blk = __shfl_sync(0xFFFFFFFFu, entry, t);
                 const uint32_t st = n_issued % PROBE_STAGES;
                 if (lane == 0) {
-                    mbar_expect_tx(&S.bar[st], BLK * 8);
+                    mbar_expect_tx(&S.bar[st], LOCAL ? BLK * 12 : BLK * 8);
                     bulk_g2s(S.kmers[st], R.arena + (size_t)blk * BLK, BLK * 8, &S.bar[st]);
+                    if (LOCAL) bulk_g2s(S.secs[st], R.sec32 + (size_t)blk * BLK, BLK * 4, &S.bar[st]);
                 }
                 n_issued++;
             };
@@ -357,13 +423,18 @@ __global__ void __launch_bounds__(PROBE_WARPS * 32, 2) k_route_probe_tma(const P
                 const uint32_t st = n_used % PROBE_STAGES, parity = (n_used / PROBE_STAGES) & 1u;
                 mbar_wait(&S.bar[st], parity);
                 uint64_t c[BLK / 32];
+                uint32_t sa[LOCAL ? BLK / 32 : 1];
 #pragma unroll
-                for (int j = 0; j < (int)(BLK / 32); j++) c[j] = S.kmers[st][32 * j + lane];
+                for (int j = 0; j < (int)(BLK / 32); j++) {
+                    c[j] = S.kmers[st][32 * j + lane];
+                    if (LOCAL) sa[LOCAL ? j : 0] = S.secs[st][32 * j + lane];
+                }
                 n_used++;
                 __syncwarp();                                                    // the stage is free again
                 if (t + PROBE_STAGES < m) issue(t + PROBE_STAGES);
                 const uint32_t blk = __shfl_sync(0xFFFFFFFFu, entry, t);
-                probe_block<LAYOUT>(p, c, R.labels + (size_t)blk * BLK, lane, probed);
+                if constexpr (LOCAL) probe_block_local(p, c, sa, R.labels + (size_t)blk * BLK, lane, probed);
+                else probe_block<LAYOUT>(p, c, R.labels + (size_t)blk * BLK, lane, probed);
             }
         }
     }
@@ -476,6 +547,7 @@ struct RouteCtx {
     uint8_t* peer[ROUTE_MAX_RANKS] = {};
     bool peer_ipc[ROUTE_MAX_RANKS] = {};
     uint32_t* pos_of = nullptr;
+    bool local = false;                       // LOCAL shards: entries are (sector, key), the scatter runs the minimizer front end
     RouteHeader* h_hdr = nullptr;             // pinned copy for stats
     int sm_count = 0;
     uint64_t last_lookups = 0, last_probed = 0, last_blocks = 0;
@@ -499,7 +571,6 @@ int route_alloc(cuclark_db* db, int n_ranks, size_t max_containers) {
     if (!db->d_table) { set_error("no database loaded"); return CUCLARK_ERR_STATE; }
     if (n_ranks < 1 || n_ranks > ROUTE_MAX_RANKS) { set_error("n_ranks must be 1..%d", ROUTE_MAX_RANKS); return CUCLARK_ERR_ARG; }
     if (db->cfg.shard_count != n_ranks) { set_error("the handle holds shard %d of %d, not of %d", db->cfg.shard_index, db->cfg.shard_count, n_ranks); return CUCLARK_ERR_ARG; }
-    if (db->view.layout == LAYOUT_LOCAL) { set_error("k-mer routing needs a hashed table layout (1 or 2)"); return CUCLARK_ERR_STATE; }
     if (max_containers == 0 || max_containers > ((size_t)1 << 28)) { set_error("max_containers must be in [1, 2^28] per call"); return CUCLARK_ERR_ARG; }
     route_free(db);
     RouteCtx* r = new RouteCtx();
@@ -511,7 +582,8 @@ int route_alloc(cuclark_db* db, int n_ranks, size_t max_containers) {
     const uint64_t blocks = (entries + (BLK - 32) - 1) / (BLK - 32) + warps * n_ranks + 64;
     if (blocks * BLK >= 0xFFFFFFFFull) { delete r; set_error("routing arena exceeds 2^32 entries: lower max_containers"); return CUCLARK_ERR_ARG; }
     r->cap_blocks = (uint32_t)blocks;
-    r->bytes = region_bytes(n_ranks, r->cap_blocks);
+    r->local = db->view.layout == LAYOUT_LOCAL;
+    r->bytes = region_bytes(n_ranks, r->cap_blocks, r->local);
     if (cudaMalloc(&r->region, r->bytes) != cudaSuccess) { cudaGetLastError(); delete r; set_error("cudaMalloc of the %.2f GB routing region failed", r->bytes / 1e9); return CUCLARK_ERR_NOMEM; }
     if (cudaMalloc(&r->pos_of, 8 * max_containers * 4) != cudaSuccess) { cudaGetLastError(); cudaFree(r->region); delete r; set_error("cudaMalloc of the position map failed"); return CUCLARK_ERR_NOMEM; }
     if (cudaMallocHost(&r->h_hdr, sizeof(RouteHeader)) != cudaSuccess) { cudaGetLastError(); cudaFree(r->region); cudaFree(r->pos_of); delete r; set_error("cudaMallocHost failed"); return CUCLARK_ERR_NOMEM; }
@@ -551,7 +623,7 @@ int route_connect(cuclark_db* const* dbs, int n) {
         if (!dbs[i] || !dbs[i]->route) { set_error("cuclark_route_alloc every handle first"); return CUCLARK_ERR_STATE; }
         RouteCtx* r = dbs[i]->route;
         if (r->n_ranks != n || r->rank != i) { set_error("handles must be passed in rank order (handle %d is rank %d of %d)", i, r->rank, r->n_ranks); return CUCLARK_ERR_ARG; }
-        if (r->cap_blocks != dbs[0]->route->cap_blocks) { set_error("all ranks must allocate the same capacity"); return CUCLARK_ERR_ARG; }
+        if (r->cap_blocks != dbs[0]->route->cap_blocks || r->local != dbs[0]->route->local) { set_error("all ranks must allocate the same capacity and hold the same table layout"); return CUCLARK_ERR_ARG; }
     }
     for (int i = 0; i < n; i++) {
         CK(cudaSetDevice(dbs[i]->cfg.device));
@@ -592,13 +664,16 @@ int route_scatter(cuclark_db* db, const uint32_t* d_ptr, const uint16_t* d_cont,
     ScatterParams p;
     p.reads_ptr = d_ptr; p.cont = d_cont; p.n_reads = (uint32_t)n_reads; p.k = db->cfg.k;
     p.M = db->view.M; p.magic = db->view.magic; p.n_ranks = r->n_ranks;
-    for (int i = 0; i <= r->n_ranks; i++) p.lo[i] = (uint64_t)((__uint128_t)p.M * i / r->n_ranks);     // choose_geometry's shard ranges
-    p.inv_width = (float)((double)r->n_ranks / (double)p.M);
+    p.NL = (uint32_t)db->view.NL; p.nl_m32 = db->view.nl_m32; p.nl_sh = db->view.nl_sh;
+    const uint64_t units = r->local ? db->view.NL : p.M;          // shards are ranges of lines (LOCAL) or of buckets: choose_geometry
+    for (int i = 0; i <= r->n_ranks; i++) p.lo[i] = (uint64_t)((__uint128_t)units * i / r->n_ranks);
+    p.inv_width = (float)((double)r->n_ranks / (double)units);
     p.mine = region_view(r->region, r->n_ranks, r->cap_blocks);
     p.cap_blocks = r->cap_blocks;
     p.pos_of = r->pos_of;
     const int blocks = (int)std::min<size_t>((n_reads + R_WARPS - 1) / R_WARPS, (size_t)r->sm_count * SCATTER_BLOCKS_PER_SM);
-    k_route_scatter<<<blocks, R_WARPS * 32, 0, st>>>(p);
+    if (r->local) k_route_scatter<true><<<blocks, R_WARPS * 32, 0, st>>>(p);
+    else k_route_scatter<false><<<blocks, R_WARPS * 32, 0, st>>>(p);
     CK(cudaGetLastError());
     count_launches(1);
     return CUCLARK_OK;
@@ -614,12 +689,16 @@ int route_probe(cuclark_db* db, cudaStream_t st) {
     for (int i = 0; i < ROUTE_MAX_RANKS; i++) p.region[i] = i < r->n_ranks ? r->peer[i] : nullptr;
     p.my_hdr = reinterpret_cast<RouteHeader*>(r->region);
     const int blocks = r->sm_count * 2;
-    static const bool use_ldg = getenv("CUCLARK_ROUTE_LDG") != nullptr;       // the register-prefetch variant, for A/B runs
-    if (use_ldg) {
+    static const bool use_ldg = getenv("CUCLARK_ROUTE_LDG") != nullptr;       // the register-prefetch variant, for A/B runs (hashed shards)
+    if (r->local) {
+        const size_t smem = sizeof(ProbeWarpSmem<true>) * PROBE_WARPS;
+        CK(cudaFuncSetAttribute(k_route_probe_tma<LAYOUT_LOCAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_route_probe_tma<LAYOUT_LOCAL><<<blocks, PROBE_WARPS * 32, smem, st>>>(p);
+    } else if (use_ldg) {
         if (db->view.layout == LAYOUT_NARROW) k_route_probe<LAYOUT_NARROW><<<blocks, 256, 0, st>>>(p);
         else k_route_probe<LAYOUT_WIDE><<<blocks, 256, 0, st>>>(p);
     } else {
-        const size_t smem = sizeof(ProbeWarpSmem) * PROBE_WARPS;
+        const size_t smem = sizeof(ProbeWarpSmem<false>) * PROBE_WARPS;
         if (db->view.layout == LAYOUT_NARROW) {
             CK(cudaFuncSetAttribute(k_route_probe_tma<LAYOUT_NARROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             k_route_probe_tma<LAYOUT_NARROW><<<blocks, PROBE_WARPS * 32, smem, st>>>(p);

@@ -76,14 +76,14 @@ def run_routed(case_k, n_targets, htsize, arrays, ptr, cont, n_ranks, row_pairs,
     return final, rows, stats, gstats, entries
 
 
-@pytest.mark.parametrize("n_ranks,layout", [(1, 0), (2, 0), (3, 2), (4, 1), (8, 0)])
+@pytest.mark.parametrize("n_ranks,layout", [(1, 0), (2, 0), (3, 2), (4, 1), (8, 0), (1, 3), (2, 3), (5, 3)])
 def test_routed_equals_oracle_one_device(oracle, light_small, n_ranks, layout):
     c = light_small
     sz, ky, lb = c.arrays
     odb = oracle.db_from_arrays(c.htsize, c.k, sz, ky, lb)
     ptr, cont, final, rows, lookups = oracle_expect(oracle, odb, c.k, c.reads_bytes, c.n_targets, c.maxhits)
     gf, gr, st, gst, entries = run_routed(c.k, c.n_targets, c.htsize, c.arrays, ptr, cont, n_ranks, c.maxhits, layout=layout)
-    assert entries == c.kmers.size
+    assert entries >= c.kmers.size if layout == 3 else entries == c.kmers.size
     assert np.array_equal(gf, final)
     assert np.array_equal(gr, rows)
     assert sum(s["lookups"] for s in st) == lookups            # every k-mer scattered once ...
@@ -116,8 +116,8 @@ def test_routed_edge_cases_and_dense_fallback(oracle):
     ]
     data = b"".join(reads)
     ptr, cont, final, rows, lookups = oracle_expect(oracle, odb, k, data, T, 15)
-    for n_ranks in (2, 16):                                    # 16 ranks over 9 reads: some ranks have no read
-        gf, gr, st, gst, _ = run_routed(k, T, HTSIZE_LIGHT, arrays, ptr, cont, n_ranks, 15)
+    for n_ranks, layout in ((2, 0), (16, 0), (3, 3)):          # 16 ranks over 9 reads: some ranks have no read; LOCAL shards
+        gf, gr, st, gst, _ = run_routed(k, T, HTSIZE_LIGHT, arrays, ptr, cont, n_ranks, 15, layout=layout)
         assert np.array_equal(gf, final), n_ranks
         assert np.array_equal(gr, rows), n_ranks
         assert sum(s["lookups"] for s in st) == lookups == sum(s["probed"] for s in st)
@@ -153,8 +153,42 @@ def test_routed_refuses_what_it_cannot_do(light_small):
             g.route_scatter(0, 0, 5, 2000)                     # more containers than allocated
 
 
-@pytest.mark.parametrize("n_ranks", [2, 4, 8])
-def test_routed_multi_gpu(oracle, light_c1, n_ranks):
+def test_routed_local_shards_low_complexity(oracle):
+    """LOCAL shards: tie k-mers (periodic sequence, two possible homes that may lie in two shards), both strands, parts
+    longer than a chunk: the scatter kernel picks the home as the single-table kernel does, exactly one shard answers."""
+    from test_gpu_local_layout import low_complexity_reads
+    from oracle.binding import key_bytes_for
+    k, T, G = 21, 6, 30_000
+    rng = np.random.default_rng(5)
+    targets = [synth.genome_codes(13, t, 0, G) for t in range(T)]
+    for t in (1, 4):
+        for _ in range(30):
+            period = int(rng.integers(1, 6))
+            pos = int(rng.integers(0, G - 200))
+            targets[t][pos:pos + 120] = np.resize(rng.integers(0, 4, period), 120)
+    kmers, labels = dbtools.build_entries(targets, k, 0)
+    arrays = dbtools.entries_to_arrays(kmers, labels, HTSIZE_LIGHT, key_bytes_for(k, HTSIZE_LIGHT))
+    odb = oracle.db_from_arrays(HTSIZE_LIGHT, k, *arrays)
+    asc = np.frombuffer(b"ACGT", np.uint8)
+    reads = []
+    for i in range(600):
+        t = int(rng.integers(0, T)); L = int(rng.integers(k - 2, 400)); pos = int(rng.integers(0, G - L))
+        codes = targets[t][pos:pos + L]
+        if i & 1:
+            codes = 3 - codes[::-1]
+        reads.append(b">r%d\n" % i + asc[codes].tobytes() + b"\n")
+    long_codes = np.concatenate([targets[2][:3000], 3 - targets[3][::-1][:2500]])
+    data = b"".join(reads) + low_complexity_reads(rng, 300, 150) + b">long\n" + asc[long_codes].tobytes() + b"\n"
+    ptr, cont, final, rows, lookups = oracle_expect(oracle, odb, k, data, T, 23)
+    for n_ranks in (2, 3, 7):
+        gf, gr, st, _, entries = run_routed(k, T, HTSIZE_LIGHT, arrays, ptr, cont, n_ranks, 23, layout=3)
+        assert entries >= kmers.size                              # tie k-mers live in the overflow table of both homes' shards
+        assert np.array_equal(gf, final) and np.array_equal(gr, rows), n_ranks
+        assert sum(s["lookups"] for s in st) == lookups == sum(s["probed"] for s in st)
+
+
+@pytest.mark.parametrize("n_ranks,layout", [(2, 0), (4, 0), (8, 0), (2, 3), (8, 3)])
+def test_routed_multi_gpu(oracle, light_c1, n_ranks, layout):
     """One process, one shard per DEVICE: k-mers and labels cross NVLink through peer pointers."""
     if n_gpus() < n_ranks:
         pytest.skip(f"needs {n_ranks} GPUs")
@@ -163,6 +197,6 @@ def test_routed_multi_gpu(oracle, light_c1, n_ranks):
     odb = oracle.db_from_arrays(c.htsize, c.k, sz, ky, lb)
     ptr, cont, final, rows, lookups = oracle_expect(oracle, odb, c.k, c.reads_bytes, c.n_targets, c.maxhits, 8)
     gf, gr, st, _, _ = run_routed(c.k, c.n_targets, c.htsize, c.arrays, ptr, cont, n_ranks, c.maxhits,
-                                  devices=list(range(n_ranks)))
+                                  devices=list(range(n_ranks)), layout=layout)
     assert np.array_equal(gf, final) and np.array_equal(gr, rows)
     assert sum(s["probed"] for s in st) == lookups
