@@ -41,7 +41,15 @@ namespace cuclark {
 
 namespace {
 
-constexpr uint32_t BLK = 256;                     // arena entries per block
+#ifndef CUCLARK_ROUTE_BLK
+#define CUCLARK_ROUTE_BLK 1024
+#endif
+// arena entries per block = one TMA bulk copy. 8 GPUs, hashed shards, probe phase per 1.2 G k-mers: 256 entries (2 KB
+// copies, 4 stages, 2 CTAs per SM) 40.2 ms; 1,024 entries (8 KB copies, 2 stages, 1 CTA per SM) 35.7 ms — the per-copy
+// cost of a remote bulk copy, not NVLink bandwidth (260 GB/s per GPU), was what the smaller blocks paid.
+constexpr uint32_t BLK = CUCLARK_ROUTE_BLK;
+constexpr uint32_t SUB = 256;                     // entries a warp holds in registers at a time while probing a block
+static_assert(BLK % SUB == 0, "block = whole sub-blocks");
 constexpr uint64_t SENTINEL = ~0ull;              // unused arena entry (never a canonical k-mer, also at k = 32)
 constexpr uint16_t LABEL_NONE = 0xFFFF;
 constexpr int R_WARPS = 8;
@@ -243,11 +251,11 @@ struct ProbeParams {
 
 // One block of 256 k-mers: probe them in this shard's table, store the labels into the asker's label array.
 template <int LAYOUT>
-__device__ __forceinline__ void probe_block(const ProbeParams& p, const uint64_t (&c)[BLK / 32], uint16_t* dst, int lane,
+__device__ __forceinline__ void probe_block(const ProbeParams& p, const uint64_t (&c)[SUB / 32], uint16_t* dst, int lane,
                                             unsigned long long& probed) {
     const TableView& T = p.t;
 #pragma unroll
-    for (int h = 0; h < (int)(BLK / 32); h += 4) {
+    for (int h = 0; h < (int)(SUB / 32); h += 4) {
         Sector sec[4];
         uint64_t q[4], b[4];
         bool live[4];
@@ -275,11 +283,11 @@ __device__ __forceinline__ void probe_block(const ProbeParams& p, const uint64_t
 // The same for a LOCAL shard: the entry is (A sector inside this shard, 37-bit key). Consecutive entries of a block
 // come from consecutive k-mers of a read, share their minimizer and so their two candidate lines: the 32 lanes'
 // loads of one round coalesce into ~14 line requests. Two entries per lane in flight (2 x 2 sectors of registers).
-__device__ __forceinline__ void probe_block_local(const ProbeParams& p, const uint64_t (&key)[BLK / 32], const uint32_t (&sa)[BLK / 32],
+__device__ __forceinline__ void probe_block_local(const ProbeParams& p, const uint64_t (&key)[SUB / 32], const uint32_t (&sa)[SUB / 32],
                                                   uint16_t* dst, int lane, unsigned long long& probed) {
     const TableView& T = p.t;
 #pragma unroll
-    for (int h = 0; h < (int)(BLK / 32); h += 2) {
+    for (int h = 0; h < (int)(SUB / 32); h += 2) {
         Sector A[2], B[2];
         bool live[2];
 #pragma unroll
@@ -307,6 +315,7 @@ __device__ __forceinline__ void probe_block_local(const ProbeParams& p, const ui
     }
 }
 
+#if CUCLARK_ROUTE_BLK == 256
 // Every warp walks its share of the block list addressed to this shard in rank g's region. The k-mers of the NEXT
 // block (and the list entry after it) are already on their way over NVLink while the current block is probed:
 // a remote load takes microseconds, and without the prefetch the probe rate fell from 33 G/s (2 GPUs, half of the
@@ -350,13 +359,16 @@ __global__ void __launch_bounds__(256, 2) k_route_probe(const ProbeParams p) {
     if (lane == 0 && probed) atomicAdd(&p.my_hdr->probed, probed);
 }
 
+#endif
+
 // ---- the same walk with the k-mer blocks brought in by the TMA (bulk async copies into shared memory) ------
 // Each warp owns a ring of PROBE_STAGES 2 KB stages and one mbarrier per stage; lane 0 arms the barrier with the
 // byte count and issues `cp.async.bulk` from the (peer) arena, the warp waits on the barrier's phase before it
 // reads the stage. Up to PROBE_STAGES blocks per warp are in flight over NVLink while one is being probed, without
 // holding them in registers. A warp takes a CONTIGUOUS range of the block list so that 32 list entries arrive
 // with one coalesced load.
-constexpr int PROBE_STAGES = 4;
+constexpr int PROBE_STAGES = BLK >= 1024 ? 2 : 4;
+constexpr int PROBE_CTAS_PER_SM = BLK >= 1024 ? 1 : 2;
 constexpr int PROBE_WARPS = 8;
 template <bool LOCAL>
 struct alignas(128) ProbeWarpSmem {
@@ -385,7 +397,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 template <int LAYOUT>
-__global__ void __launch_bounds__(PROBE_WARPS * 32, 2) k_route_probe_tma(const ProbeParams p) {
+__global__ void __launch_bounds__(PROBE_WARPS * 32, PROBE_CTAS_PER_SM) k_route_probe_tma(const ProbeParams p) {
     extern __shared__ __align__(128) uint8_t probe_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     constexpr bool LOCAL = LAYOUT == LAYOUT_LOCAL;
@@ -422,19 +434,24 @@ __global__ void __launch_bounds__(PROBE_WARPS * 32, 2) k_route_probe_tma(const P
             for (uint32_t t = 0; t < m; t++) {
                 const uint32_t st = n_used % PROBE_STAGES, parity = (n_used / PROBE_STAGES) & 1u;
                 mbar_wait(&S.bar[st], parity);
-                uint64_t c[BLK / 32];
-                uint32_t sa[LOCAL ? BLK / 32 : 1];
-#pragma unroll
-                for (int j = 0; j < (int)(BLK / 32); j++) {
-                    c[j] = S.kmers[st][32 * j + lane];
-                    if (LOCAL) sa[LOCAL ? j : 0] = S.secs[st][32 * j + lane];
-                }
-                n_used++;
-                __syncwarp();                                                    // the stage is free again
-                if (t + PROBE_STAGES < m) issue(t + PROBE_STAGES);
                 const uint32_t blk = __shfl_sync(0xFFFFFFFFu, entry, t);
-                if constexpr (LOCAL) probe_block_local(p, c, sa, R.labels + (size_t)blk * BLK, lane, probed);
-                else probe_block<LAYOUT>(p, c, R.labels + (size_t)blk * BLK, lane, probed);
+#pragma unroll 1
+                for (uint32_t sub = 0; sub < BLK; sub += SUB) {
+                    uint64_t c[SUB / 32];
+                    uint32_t sa[LOCAL ? SUB / 32 : 1];
+#pragma unroll
+                    for (int j = 0; j < (int)(SUB / 32); j++) {
+                        c[j] = S.kmers[st][sub + 32 * j + lane];
+                        if (LOCAL) sa[LOCAL ? j : 0] = S.secs[st][sub + 32 * j + lane];
+                    }
+                    if (sub + SUB == BLK) {                                       // everything read: the stage is free again
+                        n_used++;
+                        __syncwarp();
+                        if (t + PROBE_STAGES < m) issue(t + PROBE_STAGES);
+                    }
+                    if constexpr (LOCAL) probe_block_local(p, c, sa, R.labels + (size_t)blk * BLK + sub, lane, probed);
+                    else probe_block<LAYOUT>(p, c, R.labels + (size_t)blk * BLK + sub, lane, probed);
+                }
             }
         }
     }
@@ -688,15 +705,17 @@ int route_probe(cuclark_db* db, cudaStream_t st) {
     p.n_targets = (uint32_t)db->cfg.n_targets;
     for (int i = 0; i < ROUTE_MAX_RANKS; i++) p.region[i] = i < r->n_ranks ? r->peer[i] : nullptr;
     p.my_hdr = reinterpret_cast<RouteHeader*>(r->region);
-    const int blocks = r->sm_count * 2;
+    const int blocks = r->sm_count * PROBE_CTAS_PER_SM;
     static const bool use_ldg = getenv("CUCLARK_ROUTE_LDG") != nullptr;       // the register-prefetch variant, for A/B runs (hashed shards)
     if (r->local) {
         const size_t smem = sizeof(ProbeWarpSmem<true>) * PROBE_WARPS;
         CK(cudaFuncSetAttribute(k_route_probe_tma<LAYOUT_LOCAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_route_probe_tma<LAYOUT_LOCAL><<<blocks, PROBE_WARPS * 32, smem, st>>>(p);
+#if CUCLARK_ROUTE_BLK == 256
     } else if (use_ldg) {
         if (db->view.layout == LAYOUT_NARROW) k_route_probe<LAYOUT_NARROW><<<blocks, 256, 0, st>>>(p);
         else k_route_probe<LAYOUT_WIDE><<<blocks, 256, 0, st>>>(p);
+#endif
     } else {
         const size_t smem = sizeof(ProbeWarpSmem<false>) * PROBE_WARPS;
         if (db->view.layout == LAYOUT_NARROW) {
