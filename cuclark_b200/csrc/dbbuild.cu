@@ -107,22 +107,14 @@ __global__ void k_db_mark_lines(const uint8_t* __restrict__ text, uint32_t n, ui
     line_flag[p] = (p == 0 || text[p - 1] == '\n') ? 1u : 0u;
 }
 
-__global__ void __launch_bounds__(DBT) k_db_blank_headers(uint8_t* text, uint32_t n, const uint32_t* __restrict__ line_start,
-                                                          uint32_t n_lines) {
-    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (warp >= n_lines) return;
-    const uint32_t s = line_start[warp];
-    const uint32_t e = warp + 1 < n_lines ? line_start[warp + 1] - 1 : n;     // position of the '\n' (or n)
-    uint32_t from = 0xFFFFFFFFu;
-    for (uint32_t p0 = s; p0 < e; p0 += 32) {
-        const uint32_t p = p0 + lane;
-        const uint32_t m = __ballot_sync(0xFFFFFFFFu, p < e && text[p] == '>');
-        if (m) { from = p0 + __ffs(m) - 1; break; }
-    }
-    if (from == 0xFFFFFFFFu) return;
-    for (uint32_t p = from + lane; p < e && p < n; p += 32)
-        if (text[p] != '\n') text[p] = BLANK;
+// From every '>' to the end of its line the text is blanked: the reference skips from a '>' to the next newline
+// (m_table['>'] == -2, src/CuCLARK_hh.hh:956-974). One thread per byte finds the '>' (they are rare: one per record),
+// and walks its header line. (Round 1 gave every LINE a warp that searched it for a '>': a single-line 4 Mbp genome
+// was scanned by one warp, 35 ms per file and pass — 83 of the 106 s of the bacterial-scale build.)
+__global__ void __launch_bounds__(DBT) k_db_blank_headers(uint8_t* text, uint32_t n) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n || text[p] != '>') return;
+    for (uint32_t q = p; q < n && text[q] != '\n'; q++) text[q] = BLANK;      // (a second '>' of the line: its thread repeats the tail)
 }
 
 // class of a byte after header blanking: 0..3 forward code (m_table: A0 C1 G2 T/U3), 4 newline, 5 break
@@ -473,7 +465,7 @@ int scan_file(FileScratch& fs, const uint8_t* host, size_t n_bytes, int k, int l
     const uint32_t n_lines = h_small[0];
     R(fs.line_start.reserve((size_t)(n_lines + 2) * 4));
     k_db_emit_flagged<<<n_tiles, DBT, 0, st>>>(flags, n, tiles, fs.line_start.as<uint32_t>());
-    k_db_blank_headers<<<(uint32_t)(((uint64_t)n_lines * 32 + DBT - 1) / DBT), DBT, 0, st>>>(text, n, fs.line_start.as<uint32_t>(), n_lines);
+    k_db_blank_headers<<<(n + DBT - 1) / DBT, DBT, 0, st>>>(text, n);
     // compaction
     k_db_count_nt<<<n_tiles, DBT, 0, st>>>(text, n, tiles, 0, nullptr);
     k_scan_u32_tiles<<<1, DBT, 0, st>>>(tiles, n_tiles, fs.d_small + 1);
