@@ -34,7 +34,7 @@ constexpr double OVF_LOAD = 0.75;                  // mean entries per 3-slot ov
 constexpr double OVF_LOAD_LOCAL = 1.2;             // LOCAL spills ~13% of the entries: a denser overflow table
 constexpr int CHUNK_THREADS = 1024;
 constexpr uint32_t CHUNK_BLOCKS = 8192;            // 8.4M reference buckets per chunk
-constexpr int LOAD_IO_THREADS = 8;                 // host threads filling a staging set of the file loader
+constexpr int LOAD_IO_THREADS = 12;                // host threads filling a staging set of the file loader
 
 struct BuildCtx {
     uint4* table;
