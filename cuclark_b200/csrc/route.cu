@@ -367,9 +367,18 @@ __global__ void __launch_bounds__(256, 2) k_route_probe(const ProbeParams p) {
 // reads the stage. Up to PROBE_STAGES blocks per warp are in flight over NVLink while one is being probed, without
 // holding them in registers. A warp takes a CONTIGUOUS range of the block list so that 32 list entries arrive
 // with one coalesced load.
-constexpr int PROBE_STAGES = BLK >= 1024 ? 2 : 4;
-constexpr int PROBE_CTAS_PER_SM = BLK >= 1024 ? 1 : 2;
-constexpr int PROBE_WARPS = 8;
+#ifndef CUCLARK_PROBE_STAGES
+#define CUCLARK_PROBE_STAGES (CUCLARK_ROUTE_BLK >= 1024 ? 2 : 4)
+#endif
+#ifndef CUCLARK_PROBE_CTAS
+#define CUCLARK_PROBE_CTAS (CUCLARK_ROUTE_BLK >= 1024 ? 1 : 2)
+#endif
+#ifndef CUCLARK_PROBE_WARPS
+#define CUCLARK_PROBE_WARPS 8
+#endif
+constexpr int PROBE_STAGES = CUCLARK_PROBE_STAGES;
+constexpr int PROBE_CTAS_PER_SM = CUCLARK_PROBE_CTAS;
+constexpr int PROBE_WARPS = CUCLARK_PROBE_WARPS;
 template <bool LOCAL>
 struct alignas(128) ProbeWarpSmem {
     uint64_t kmers[PROBE_STAGES][BLK];
