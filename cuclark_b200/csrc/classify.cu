@@ -47,9 +47,6 @@ constexpr int ILP_ROUNDS = 4;         // independent probes per lane
 #ifndef CUCLARK_LOCAL_SKIP_EMPTY_ROW
 #define CUCLARK_LOCAL_SKIP_EMPTY_ROW 1      // the look-ahead row of a part's last group usually holds no m-mer: do not hash it
 #endif
-#ifndef CUCLARK_LOCAL_PIPELINE
-#define CUCLARK_LOCAL_PIPELINE 0            // 1: prefetch a row's two sectors into L2 and probe them one row later
-#endif
 #ifndef CUCLARK_LOCAL_MIN_BLOCKS
 #define CUCLARK_LOCAL_MIN_BLOCKS 4
 #endif
@@ -57,10 +54,6 @@ constexpr int ILP_LOCAL = CUCLARK_ILP_LOCAL;                // LOCAL layout: row
 constexpr int LOCAL_MIN_BLOCKS = CUCLARK_LOCAL_MIN_BLOCKS;  // resident blocks per SM asked of ptxas for the LOCAL kernel
 constexpr int READS_PER_CHUNK = 31;   // one coalesced load of 32 container offsets delimits 31 reads
 constexpr int COUNTER_CHUNK = 4;      // dynamic work counter (reset with the other counters)
-
-#if CUCLARK_LOCAL_PIPELINE
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-#endif
 
 struct ClassifyParams {
     TableView t;
@@ -163,31 +156,6 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, LAYOUT == LAYOUT_LOCAL ?
                     uint64_t carry_z = 0, carry_c = 0;       // carry_z bit 61: the k-mer stands in its canonical form
                     uint32_t carry_oh = 0;
                     const int m_limit = (int)L - (k - LOCAL_W + 1) - cb - lane;   // an m-mer starts at row i iff 32 i <= m_limit
-#if CUCLARK_LOCAL_PIPELINE
-                    // LOCAL, pipelined: the two sectors of a row are asked into L2 (a prefetch holds no register) as soon as
-                    // their addresses are known and are read one row later, behind the address arithmetic of the next row
-                    static_assert(LAYOUT != LAYOUT_LOCAL || ILP == 1, "the pipelined LOCAL probe handles one row per group");
-                    uint32_t pd_sa = 0, pd_sb = 0, pd_qlo = 0, pd_qhi = 0;   // pd_qhi bit 31: the lane has a k-mer
-                    int pd_row = -1;                                          // warp-uniform: the row waiting for its probe
-                    auto probe_pending = [&]() {
-                        const bool lv = pd_qhi >> 31;
-                        const uint64_t qq = (uint64_t)pd_qlo | ((uint64_t)(pd_qhi & 0x7FFFFFFFu) << 32);
-                        const Sector A = load_sector_line(T.buckets + 2 * (uint64_t)pd_sa);
-                        const Sector B = load_sector_line(T.buckets + 2 * (uint64_t)pd_sb);
-                        const uint32_t la_ = match_sector<LAYOUT_LOCAL>(A, qq);
-                        const uint32_t lb_ = match_sector<LAYOUT_LOCAL>(B, qq | ((uint64_t)LOCAL_ALT_BIT << 32));
-                        uint32_t label = la_ == NO_LABEL ? lb_ : la_;
-                        const bool ask_ovf = lv && label == NO_LABEL && sector_overflowed(A) && sector_overflowed(B);
-                        if (__any_sync(0xFFFFFFFFu, ask_ovf)) {
-                            // rare: the overflow table is keyed by the k-mer itself, which was not kept: cut it out of the words again
-                            const uint64_t hi = shfl64(W, pd_row & 31), lo = shfl64(W, (pd_row + 1) & 31);
-                            const uint64_t x = window64(hi, lo, 2 * lane) >> kshift;
-                            if (ask_ovf) label = ovf_lookup(T, canonical(x, k));
-                        }
-                        if (!lv || label >= p.n_targets) label = NO_LABEL;
-                        hits.add(label, tkey, tcnt, lane);
-                    };
-#endif
                     for (int r0 = 0; r0 < rounds; r0 += ILP) {
                         uint64_t q[ILP];
                         uint32_t lb[ILP];
@@ -278,18 +246,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, LAYOUT == LAYOUT_LOCAL ?
                                 live[j] = valid && lb64 < T.n_local;
                                 my_lookups += valid;
                                 const uint32_t rel_b = local_alt_rel(line - T.line_lo, zq, T.line_n, false);
-#if CUCLARK_LOCAL_PIPELINE
-                                {
-                                    const uint32_t sa_ = live[j] ? lb[j] : 0u;                           // (n_local < 2^32 sectors)
-                                    const uint32_t sb_ = live[j] ? rel_b * 4u + (uint32_t)(o_c & 3) : 0u;
-                                    prefetch_l2(T.buckets + 2 * (uint64_t)sa_);
-                                    prefetch_l2(T.buckets + 2 * (uint64_t)sb_);
-                                    if (pd_row >= 0) probe_pending();                                    // the previous row, now in L2
-                                    pd_sa = sa_; pd_sb = sb_; pd_qlo = (uint32_t)q[j];
-                                    pd_qhi = (uint32_t)(q[j] >> 32) | ((uint32_t)live[j] << 31);
-                                    pd_row = i;
-                                }
-#elif CUCLARK_LOCAL_BRANCHFREE
+#if CUCLARK_LOCAL_BRANCHFREE
                                 // no branch around the loads: a lane without a k-mer (tail of a part, other shard) reads sector 0
                                 const uint64_t sa_ = live[j] ? (uint64_t)lb[j] : 0ull;
                                 const uint64_t sb_ = live[j] ? (uint64_t)rel_b * 4 + (uint64_t)(o_c & 3) : 0ull;
@@ -303,7 +260,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, LAYOUT == LAYOUT_LOCAL ?
 #endif
                             }
 #pragma unroll
-                            for (int j = 0; j < (CUCLARK_LOCAL_PIPELINE ? 0 : ILP); j++) {
+                            for (int j = 0; j < ILP; j++) {
                                 uint32_t label = NO_LABEL;
 #if CUCLARK_LOCAL_BRANCHFREE
                                 {
@@ -355,9 +312,6 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, LAYOUT == LAYOUT_LOCAL ?
                             }
                         }
                     }
-#if CUCLARK_LOCAL_PIPELINE
-                    if (LAYOUT == LAYOUT_LOCAL && pd_row >= 0) probe_pending();      // the last row of these words
-#endif
                 }
                 first_part = false;
             }
